@@ -1,0 +1,15 @@
+"""irsde_b200: B200-native (sm_100a) IR-SDE / Denoising-SDE reverse-diffusion sampler.
+
+Public surface mirrors the reference (Algolzw/image-restoration-sde):
+  * ``IRSDE`` / ``DenoisingSDE``            <- codes/utils/sde_utils.py
+  * ``ConditionalUNet`` / ``DenoisingUNet``  <- codes/config/*/models/modules/DenoisingUNet_arch.py
+Importing the package does not need a GPU; running anything does (no CPU fallback).
+"""
+from . import _lib
+from .sde import IRSDE, DenoisingSDE
+from .unet import ConditionalUNet, DenoisingUNet, unet_param_shapes
+from .dist import shard_range, sharded_reverse, broadcast_weights
+
+__all__ = ["IRSDE", "DenoisingSDE", "ConditionalUNet", "DenoisingUNet", "unet_param_shapes", "shard_range",
+           "sharded_reverse", "broadcast_weights", "_lib"]
+__version__ = "0.1"

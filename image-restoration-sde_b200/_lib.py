@@ -1,0 +1,111 @@
+"""ctypes binding of libirsde_b200.so (the C ABI in include/irsde_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing, or there is no sm_100 device, calls
+raise.  ``load()`` only dlopens (works without a GPU, used by the symbol-export test).
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libirsde_b200.so")
+
+PREC_FP32, PREC_BF16 = 0, 1
+NET_CONDITIONAL, NET_DENOISING = 0, 1
+MODE_SDE, MODE_ODE, MODE_POSTERIOR, MODE_DSDE_SDE, MODE_DSDE_ODE = range(5)
+NUM_COEF = 8
+
+# every symbol include/irsde_b200.h declares
+SYMBOLS = ["irsde_create", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
+           "irsde_finalize_weights", "irsde_set_schedule", "irsde_set_coeffs", "irsde_noise_fn", "irsde_step",
+           "irsde_reverse", "irsde_noise_state", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d"]
+
+
+class Config(ctypes.Structure):
+    _fields_ = [("in_nc", ctypes.c_int32), ("out_nc", ctypes.c_int32), ("nf", ctypes.c_int32),
+                ("depth", ctypes.c_int32), ("variant", ctypes.c_int32), ("precision", ctypes.c_int32),
+                ("device", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "irsde_b200: %s not found. Build it with `python image-restoration-sde_b200/build.py` "
+            "(needs nvcc with sm_100a support). There is no CPU / PyTorch fallback." % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, u64, fp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_float)
+    L.irsde_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
+    L.irsde_create.restype = ctypes.c_int
+    L.irsde_destroy.argtypes = [vp]
+    L.irsde_destroy.restype = None
+    L.irsde_last_error.argtypes = [vp]
+    L.irsde_last_error.restype = ctypes.c_char_p
+    L.irsde_version.argtypes = []
+    L.irsde_version.restype = ctypes.c_char_p
+    L.irsde_load_tensor.argtypes = [vp, ctypes.c_char_p, vp, i32, ctypes.POINTER(i64)]
+    L.irsde_load_tensor.restype = ctypes.c_int
+    L.irsde_finalize_weights.argtypes = [vp]
+    L.irsde_finalize_weights.restype = ctypes.c_int
+    L.irsde_set_schedule.argtypes = [vp, fp, fp, fp, fp, ctypes.c_float, ctypes.c_float, i32]
+    L.irsde_set_schedule.restype = ctypes.c_int
+    L.irsde_set_coeffs.argtypes = [vp, i32, fp, i32]
+    L.irsde_set_coeffs.restype = ctypes.c_int
+    L.irsde_noise_fn.argtypes = [vp, vp, vp, fp, i32, vp, i32, i32, i32, vp]
+    L.irsde_noise_fn.restype = ctypes.c_int
+    L.irsde_step.argtypes = [vp, i32, vp, vp, vp, vp, i32, vp, i64, vp]
+    L.irsde_step.restype = ctypes.c_int
+    L.irsde_reverse.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, i32, u64, i32, vp]
+    L.irsde_reverse.restype = ctypes.c_int
+    L.irsde_noise_state.argtypes = [vp, vp, vp, i64, u64, vp]
+    L.irsde_noise_state.restype = ctypes.c_int
+    L.irsde_launch_count.argtypes = [vp]
+    L.irsde_launch_count.restype = i64
+    L.irsde_device_bytes.argtypes = [vp]
+    L.irsde_device_bytes.restype = i64
+    L.irsde_conv2d.argtypes = [vp, i32, vp, vp, vp, vp] + [i32] * 11 + [vp]
+    L.irsde_conv2d.restype = ctypes.c_int
+    _lib = L
+    return L
+
+
+class IrsdeError(RuntimeError):
+    pass
+
+
+def check(rc, ctx=None):
+    if rc != 0:
+        msg = load().irsde_last_error(ctx)
+        raise IrsdeError("irsde_b200 error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+def float_array(seq):
+    arr = (ctypes.c_float * len(seq))(*[float(v) for v in seq])
+    return arr
+
+
+class Context:
+    """Owns one ``irsde_ctx`` (one per model per device)."""
+
+    def __init__(self, in_nc, out_nc, nf, depth, variant, precision, device_index, force_simt=False):
+        L = load()
+        cfg = Config(in_nc, out_nc, nf, depth, variant, precision, device_index, 1 if force_simt else 0)
+        h = ctypes.c_void_p()
+        check(L.irsde_create(ctypes.byref(cfg), ctypes.byref(h)))
+        self.h = h
+        self.L = L
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.irsde_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,119 @@
+// Shared declarations for the irsde_b200 native library (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+namespace irsde {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- small device helpers -------------------------------------------------------------------
+__device__ __forceinline__ float to_f(float v) { return v; }
+__device__ __forceinline__ float to_f(bf16 v) { return __bfloat162float(v); }
+template <typename T>
+__device__ __forceinline__ T from_f(float v);
+template <>
+__device__ __forceinline__ float from_f<float>(float v) { return v; }
+template <>
+__device__ __forceinline__ bf16 from_f<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.0f + expf(-v)); }
+
+// A strided NHWC view: element (b,h,w,c) lives at p[((b*H + h)*W + w)*pitch + c].
+struct View {
+  void* p;
+  int pitch;  // channel pitch of the underlying buffer (elements)
+  int C;      // channels visible through the view
+};
+
+// ---- epilogue description shared by both conv engines ---------------------------------------
+struct Epilogue {
+  const float* bias;      // [Cout] or null
+  const float* ss;        // time-modulation table base ([rows][ss_S]) or null
+  const int* t_ptr;       // device int: current table row (null => row 0)
+  int ss_S;               // row length of the table
+  int ss_off;             // offset of this block's (scale[Cout], shift[Cout]) inside a row
+  int ss_img_stride;      // rows per image (0 = shared time, 1 = per-image time)
+  int silu;               // apply SiLU after modulation
+  const void* res;        // residual view (same dtype as output) or null
+  int res_pitch;
+};
+
+// ---- launch bookkeeping ------------------------------------------------------------------------
+struct LaunchCounter {
+  long long n = 0;
+};
+
+// ---- SIMT conv (conv_simt.cu) -----------------------------------------------------------------
+struct ConvGeom {
+  int B, Hin, Win, Cin;  // Hin/Win are the stored input size (before nearest upsample)
+  int up;                // 1 or 2: nearest-neighbour upsample folded into the gather
+  int KH, KW, stride, pad;
+  int Hout, Wout, Cout;
+};
+// in/out dtype T (float or bf16), weights fp32 [KH*KW][Cin][Cout]; out_nchw != null writes fp32
+// NCHW cropped to (cropH, cropW) instead of the NHWC view.
+template <typename T>
+void launch_conv_simt(const ConvGeom& g, const T* in, int in_pitch, const float* w, const Epilogue& ep, T* out,
+                      int out_pitch, float* out_nchw, int cropH, int cropW, cudaStream_t st);
+
+// ---- elementwise / reduction kernels (elementwise.cu) -----------------------------------------
+template <typename T>
+void launch_prep_input(const float* xt, const float* cond, T* out, int B, int C, int H, int W, int Hp, int Wp,
+                       int out_pitch, int conditional, cudaStream_t st);
+template <typename T>
+void launch_nchw_to_nhwc(const float* in, T* out, int B, int C, int H, int W, int out_pitch, cudaStream_t st);
+template <typename T>
+void launch_nhwc_to_nchw(const T* in, int in_pitch, float* out, int B, int C, int H, int W, cudaStream_t st);
+// channel LayerNorm (eps 1e-5) * g (+ residual)
+template <typename T>
+void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int res_pitch, T* out, int out_pitch,
+                      long long npix, int C, cudaStream_t st);
+// linear attention: qkv [B,N,384] -> ctx [B,4,32,32] (fp32) -> hidden [B,N,128]
+template <typename T>
+void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
+                    cudaStream_t st);
+size_t linattn_partial_floats(int B, int N);
+// full softmax attention (denoising-sde mid_attn): qkv [B,N,384] -> hidden [B,N,128]
+template <typename T>
+void launch_fullattn(const T* qkv, int qkv_pitch, T* hidden, int hid_pitch, int B, int N, cudaStream_t st);
+// time embedding: times[rows] -> table[rows][S]
+void launch_time_table(const float* times, int rows, int nf, const float* w1, const float* b1, const float* w2,
+                       const float* b2, const float* wall, const float* ball, int S, float* temb_ws, float* table,
+                       cudaStream_t st);
+// sampler update
+struct StepState {
+  int t;               // current timestep (table row)
+  int i;               // executed-step index (z slice)
+  const float* z;      // pre-drawn noise [T][n] or null (in-kernel Philox)
+  unsigned long long seed;
+};
+void launch_sde_update(int mode, const float* x, const float* mu, const float* noise, const float* z, long long z_stride,
+                       const float* coef, const StepState* st_dev, int t_host, float* out, long long n, uint64_t seed,
+                       cudaStream_t st);
+void launch_advance_step(StepState* st_dev, cudaStream_t st);
+void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned long long seed, cudaStream_t st);
+void launch_noise_state(const float* mu, float* out, long long n, float max_sigma, uint64_t seed, cudaStream_t st);
+// layout helpers for the tensor-core path
+template <typename T>
+void launch_space_to_depth(const T* in, int in_pitch, T* out, int B, int H, int W, int C, cudaStream_t st);
+
+// ---- tcgen05 tap-GEMM conv (conv_tc.cu) ---------------------------------------------------------
+struct TcTap {
+  int dh, dw;   // pixel offset of this tap in the A tensor
+  int plane;    // 5th coordinate of the A tensor map (space-to-depth plane), 0 otherwise
+};
+struct TcConvDesc;  // opaque: tensor maps + tap table + tile config
+TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win, int Cin, int planes,
+                           const bf16* wpacked /*[phase][tap][Cout][Cin]*/, int Cout, int ntaps, const TcTap* taps,
+                           int nphases /*1 or 4 (upsample phases)*/, const Epilogue& ep, bf16* out, int out_pitch,
+                           int Hout, int Wout, std::string* err);
+void tc_conv_destroy(TcConvDesc*);
+void tc_conv_set_runtime(TcConvDesc*, const float* ss, const int* t_ptr, int ss_img_stride);
+int tc_conv_launch(TcConvDesc*, cudaStream_t st);  // returns number of launches (1), <0 on error
+bool tc_init(std::string* err);                    // resolves cuTensorMapEncodeTiled
+
+}  // namespace irsde

@@ -1,0 +1,439 @@
+// tcgen05 "tap-GEMM" convolution for sm_100a: bf16 NHWC activations, bf16 weights, fp32 accumulate in
+// TMEM.
+//
+//   D[pixel, n] = sum_{tap} sum_{c} A[pixel + (dh,dw)_tap, c] * Wt[phase][tap][n][c]
+//
+// One CTA computes a 128-pixel x BN-channel tile.  The 128 pixels are a BW x BH patch of one image
+// (BW*BH = 128), so that for every tap the A operand is ONE TMA box {64 ch, BW, BH} of the NHWC
+// tensor shifted by (dw,dh): zero padding is the TMA out-of-bounds fill, im2col never exists in
+// memory.  The box lands in shared memory as 128 rows x 128 B with the 128B swizzle, which is exactly
+// the canonical K-major UMMA operand layout; the weights tile ({64 ch, BN} of [tap][Cout][Cin]) likewise.
+// This one kernel serves: 3x3 (9 taps), 1x1 (1 tap), 4x4/s2 (16 taps over 4 space-to-depth planes),
+// nearest-x2-upsample + 3x3 (4 output phases x 4 taps with pre-summed weights).
+//
+// Warp roles (192 threads): warp 0 = TMEM alloc + TMA producer, warp 1 = MMA issuer (one elected
+// lane), warps 2..5 = epilogue (tcgen05.ld -> bias / (scale+1)*x+shift / SiLU / +residual -> bf16 ->
+// 16-byte global stores at the channel offset of the destination concat buffer).
+// Pipeline: STAGES-deep smem ring with full/empty mbarriers; tcgen05.commit releases slots.
+// Two CTAs are co-resident per SM for BN<=128 so one CTA's epilogue overlaps the other's main loop.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace irsde {
+
+namespace {
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+struct TcParams {
+  int B, H, W;          // pixel grid enumerated by the tiles (== A tensor spatial size)
+  int Cin, Cout;
+  int ntaps, kchunks;
+  int BW, BH, logBW;
+  int tilesW, tilesH;
+  int nphases;
+  int Hout, Wout, os;   // output spatial size and output stride (2 for the upsample phases)
+  bf16* out;
+  int out_pitch;
+  const bf16* res;
+  int res_pitch;
+  const float* bias;
+  const float* ss;
+  const int* t_ptr;
+  int ss_S, ss_off, ss_img_stride, silu;
+  TcTap taps[16];
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (fails the launch) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  long long t0 = 0;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0xfffu) == 0) {
+      long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) {  // ~2 s
+        printf("irsde conv_tc: mbarrier wait timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+        __trap();
+      }
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// SM100 shared-memory matrix descriptor: K-major operand, 128B swizzle, rows of 128 bytes,
+// 8-row core groups 1024 B apart (SBO), descriptor version 1.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
+  d |= (uint64_t)(0) << 16;                           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;        // stride byte offset
+  d |= (uint64_t)1 << 46;                             // version = 1 (sm_100)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M x N.
+__device__ __forceinline__ uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16
+
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = (BN == 128) ? 3 : 4;
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int EPI_FLOATS = 3 * BN;  // mult, add, bias
+  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 256 /*barriers*/;
+  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                      const __grid_constant__ CUtensorMap map_b,
+                                                      const __grid_constant__ TcParams P) {
+  using Cfg = TcCfg<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::EPI_FLOATS);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* accum_bar = bars + 2 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // ---- tile coordinates
+  int bx = blockIdx.x;
+  const int tw_i = bx % P.tilesW; bx /= P.tilesW;
+  const int th_i = bx % P.tilesH; bx /= P.tilesH;
+  const int b = bx % P.B;
+  const int phase = bx / P.B;
+  const int py = phase >> 1, px = phase & 1;
+  const int h0 = th_i * P.BH, w0 = tw_i * P.BW;
+  const int n0 = blockIdx.y * BN;
+  const int KI = P.ntaps * P.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_b);
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int tap = 0; tap < P.ntaps; ++tap) {
+        const int dh = P.taps[tap].dh + (P.nphases == 4 ? py : 0);
+        const int dw = P.taps[tap].dw + (P.nphases == 4 ? px : 0);
+        const int plane = P.taps[tap].plane;
+        for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
+          const int s = it % STAGES;
+          if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+          tma_load_5d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, w0 + dw, h0 + dh, b, plane);
+          tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, n0, phase * P.ntaps + tap);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BN);
+      for (int it = 0; it < KI; ++it) {
+        const int s = it % STAGES;
+        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+        const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < 4; ++k)  // 4 x (K=16) per 64-channel chunk: +32 B inside the swizzle atom
+          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(accum_bar);        // accumulator complete
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int et = threadIdx.x - 64;  // 0..127
+    {
+      const int trow = P.t_ptr ? *P.t_ptr : 0;
+      const float* ssrow = P.ss ? P.ss + (long long)(trow + b * P.ss_img_stride) * P.ss_S + P.ss_off : nullptr;
+      for (int j = et; j < BN; j += 128) {
+        const int n = n0 + j;
+        float mult = 1.f, add = 0.f, bias = 0.f;
+        if (n < P.Cout) {
+          if (ssrow) { mult = ssrow[n] + 1.0f; add = ssrow[P.Cout + n]; }
+          if (P.bias) bias = P.bias[n];
+        }
+        s_epi[j] = mult; s_epi[BN + j] = add; s_epi[2 * BN + j] = bias;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
+    }
+    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
+    const int m = quad * 32 + lane;       // accumulator row == pixel index inside the tile
+    const int hh = h0 + (m >> P.logBW), ww = w0 + (m & (P.BW - 1));
+    const bool pvalid = hh < P.H && ww < P.W;
+    const long long opix = ((long long)b * P.Hout + (hh * P.os + py)) * P.Wout + (ww * P.os + px);
+    bf16* orow = P.out + opix * P.out_pitch + n0;
+    const bf16* rrow = P.res ? P.res + opix * P.res_pitch + n0 : nullptr;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
+      if (pvalid) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {  // groups of 8 channels = one 16-byte store
+          const int cg = c0 + g * 8;
+          if (n0 + cg < P.Cout) {
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = __uint_as_float(v[g * 8 + j]);
+              x = (x + s_epi[2 * BN + cg + j]) * s_epi[cg + j] + s_epi[BN + cg + j];
+              if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
+              f[j] = x;
+            }
+            if (rrow) {
+              uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[2 * j] += __low2float(r2[j]);
+                f[2 * j + 1] += __high2float(r2[j]);
+              }
+            }
+            uint4 o;
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+            *reinterpret_cast<uint4*>(orow + cg) = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+}  // namespace
+
+struct TcConvDesc {
+  CUtensorMap map_a, map_b;
+  TcParams P;
+  int BN;
+  dim3 grid;
+};
+
+bool tc_init(std::string* err) {
+  if (g_encode) return true;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+    if (err) *err = "cuTensorMapEncodeTiled not available from the driver";
+    return false;
+  }
+  g_encode = (EncodeTiledFn)fn;
+  cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+  cudaError_t le = cudaGetLastError();
+  if (le != cudaSuccess) {
+    if (err) *err = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(le);
+    g_encode = nullptr;
+    return false;
+  }
+  return true;
+}
+
+TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win, int Cin, int planes,
+                           const bf16* wpacked, int Cout, int ntaps, const TcTap* taps, int nphases, const Epilogue& ep,
+                           bf16* out, int out_pitch, int Hout, int Wout, std::string* err) {
+  auto bad = [&](const char* m) -> TcConvDesc* {
+    if (err) *err = m;
+    return nullptr;
+  };
+  if (!g_encode) return bad("tc_init not called");
+  if (ntaps < 1 || ntaps > 16) return bad("ntaps out of range");
+  if (Cin % 8 || Cout % 8 || in_pitch % 8 || out_pitch % 8) return bad("channel counts / pitches must be multiples of 8");
+  if (((uintptr_t)in & 15) || ((uintptr_t)wpacked & 15) || ((uintptr_t)out & 15)) return bad("operands must be 16-byte aligned");
+  if (ep.res && (((uintptr_t)ep.res & 15) || ep.res_pitch % 8)) return bad("residual must be 16-byte aligned");
+  TcConvDesc* d = new TcConvDesc();
+  TcParams& P = d->P;
+  memset(&P, 0, sizeof P);
+  P.B = B; P.H = Hin; P.W = Win; P.Cin = Cin; P.Cout = Cout;
+  P.ntaps = ntaps; P.kchunks = (Cin + 63) / 64;
+  P.nphases = nphases;
+  P.Hout = Hout; P.Wout = Wout; P.os = nphases == 4 ? 2 : 1;
+  P.out = out; P.out_pitch = out_pitch;
+  P.res = (const bf16*)ep.res; P.res_pitch = ep.res_pitch;
+  P.bias = ep.bias; P.ss = ep.ss; P.t_ptr = ep.t_ptr; P.ss_S = ep.ss_S; P.ss_off = ep.ss_off;
+  P.ss_img_stride = ep.ss_img_stride; P.silu = ep.silu;
+  for (int i = 0; i < ntaps; ++i) P.taps[i] = taps[i];
+  // tile shape: BW x BH = 128 pixels, minimise padded work
+  long long best = -1;
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    int bh = 128 / bw;
+    long long cost = (long long)((Win + bw - 1) / bw) * bw * ((Hin + bh - 1) / bh) * bh;
+    if (best < 0 || cost < best) { best = cost; P.BW = bw; P.BH = bh; }
+  }
+  P.logBW = 0;
+  while ((1 << P.logBW) < P.BW) P.logBW++;
+  P.tilesW = (Win + P.BW - 1) / P.BW;
+  P.tilesH = (Hin + P.BH - 1) / P.BH;
+  int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
+  d->BN = BN;
+  d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
+  // A: [planes][B][H][W][C] (C contiguous, pixel pitch in_pitch)
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B, (cuuint64_t)planes};
+    cuuint64_t strides[4] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)Win * in_pitch * 2, (cuuint64_t)Hin * Win * in_pitch * 2,
+                             (cuuint64_t)B * Hin * Win * in_pitch * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(&d->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete d;
+      if (err) { char b[96]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(A) failed: %d", (int)r); *err = b; }
+      return nullptr;
+    }
+  }
+  // B: [phase*ntaps][Cout][Cin]
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(nphases * ntaps)};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(&d->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)wpacked, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete d;
+      if (err) { char b[96]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(B) failed: %d", (int)r); *err = b; }
+      return nullptr;
+    }
+  }
+  return d;
+}
+
+void tc_conv_destroy(TcConvDesc* d) { delete d; }
+
+void tc_conv_set_runtime(TcConvDesc* d, const float* ss, const int* t_ptr, int ss_img_stride) {
+  d->P.ss = ss;
+  d->P.t_ptr = t_ptr;
+  d->P.ss_img_stride = ss_img_stride;
+}
+
+int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
+  switch (d->BN) {
+    case 32: conv_tc_kernel<32><<<d->grid, 192, TcCfg<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
+    case 64: conv_tc_kernel<64><<<d->grid, 192, TcCfg<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
+    case 128: conv_tc_kernel<128><<<d->grid, 192, TcCfg<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
+    default: conv_tc_kernel<256><<<d->grid, 192, TcCfg<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
+  }
+  return 1;
+}
+
+}  // namespace irsde

@@ -1,0 +1,595 @@
+// Memory-bound kernels of the IR-SDE hot path: input packing, channel LayerNorm, linear / full
+// attention, timestep-embedding table, and the fused sampler update.  All fp32 math; activations
+// are float (parity mode) or bf16 (perf mode).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace irsde {
+
+// =============================================================================================
+// input packing: x = cat(xt - cond, cond) with reflect pad (bottom/right) -> NHWC
+// reference: DenoisingUNet_arch.py:78-83 (check_image_size), :90-94
+// =============================================================================================
+template <typename T>
+__global__ void prep_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond, T* __restrict__ out,
+                                  int B, int C, int H, int W, int Hp, int Wp, int pitch, int conditional) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Hp * Wp;
+  if (idx >= total) return;
+  int wp = idx % Wp;
+  int hp = (idx / Wp) % Hp;
+  int b = idx / ((long long)Wp * Hp);
+  int h = hp < H ? hp : 2 * (H - 1) - hp;  // reflect (no edge repeat)
+  int w = wp < W ? wp : 2 * (W - 1) - wp;
+  T* o = out + idx * pitch;
+  for (int c = 0; c < C; ++c) {
+    long long s = (((long long)b * C + c) * H + h) * W + w;
+    float xv = xt[s];
+    if (conditional) {
+      float cv = cond[s];
+      o[c] = from_f<T>(__fsub_rn(xv, cv));
+      o[C + c] = from_f<T>(cv);
+    } else {
+      o[c] = from_f<T>(xv);
+    }
+  }
+  for (int c = conditional ? 2 * C : C; c < pitch; ++c) o[c] = from_f<T>(0.f);
+}
+
+template <typename T>
+void launch_prep_input(const float* xt, const float* cond, T* out, int B, int C, int H, int W, int Hp, int Wp,
+                       int out_pitch, int conditional, cudaStream_t st) {
+  long long total = (long long)B * Hp * Wp;
+  prep_input_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xt, cond, out, B, C, H, W, Hp, Wp, out_pitch,
+                                                                         conditional);
+}
+template void launch_prep_input<float>(const float*, const float*, float*, int, int, int, int, int, int, int, int,
+                                       cudaStream_t);
+template void launch_prep_input<bf16>(const float*, const float*, bf16*, int, int, int, int, int, int, int, int,
+                                      cudaStream_t);
+
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int C, int H, int W,
+                                    int pitch) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * W;
+  if (idx >= total) return;
+  long long hw = idx % ((long long)H * W);
+  int b = idx / ((long long)H * W);
+  for (int c = 0; c < C; ++c) out[idx * pitch + c] = from_f<T>(in[((long long)b * C + c) * H * W + hw]);
+  for (int c = C; c < pitch; ++c) out[idx * pitch + c] = from_f<T>(0.f);
+}
+template <typename T>
+void launch_nchw_to_nhwc(const float* in, T* out, int B, int C, int H, int W, int out_pitch, cudaStream_t st) {
+  long long total = (long long)B * H * W;
+  nchw_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, C, H, W, out_pitch);
+}
+template void launch_nchw_to_nhwc<float>(const float*, float*, int, int, int, int, int, cudaStream_t);
+template void launch_nchw_to_nhwc<bf16>(const float*, bf16*, int, int, int, int, int, cudaStream_t);
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int pitch, float* __restrict__ out, int B, int C, int H,
+                                    int W) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * H * W;
+  if (idx >= total) return;
+  long long hw = idx % ((long long)H * W);
+  int b = idx / ((long long)H * W);
+  for (int c = 0; c < C; ++c) out[((long long)b * C + c) * H * W + hw] = to_f(in[idx * pitch + c]);
+}
+template <typename T>
+void launch_nhwc_to_nchw(const T* in, int in_pitch, float* out, int B, int C, int H, int W, cudaStream_t st) {
+  long long total = (long long)B * H * W;
+  nhwc_to_nchw_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, in_pitch, out, B, C, H, W);
+}
+template void launch_nhwc_to_nchw<float>(const float*, int, float*, int, int, int, int, cudaStream_t);
+template void launch_nhwc_to_nchw<bf16>(const bf16*, int, float*, int, int, int, int, cudaStream_t);
+
+// =============================================================================================
+// channel LayerNorm: (x-mean)*rsqrt(var_biased+1e-5)*g (+ residual)   module_util.py:70-79,20-26
+// one warp per pixel, two-pass statistics (matches torch.var(unbiased=False) numerics closely)
+// =============================================================================================
+template <typename T>
+__global__ void layernorm_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
+                                 const T* __restrict__ res, int res_pitch, T* __restrict__ out, int out_pitch,
+                                 long long npix, int C) {
+  int lane = threadIdx.x & 31;
+  long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const T* xr = x + pix * x_pitch;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += to_f(xr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    float d = to_f(xr[c]) - mean;
+    v += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  float rstd = 1.0f / sqrtf(v / (float)C + 1e-5f);
+  T* orow = out + pix * out_pitch;
+  const T* rr = res ? res + pix * res_pitch : nullptr;
+  for (int c = lane; c < C; c += 32) {
+    float y = (to_f(xr[c]) - mean) * rstd * g[c];
+    if (rr) y += to_f(rr[c]);
+    orow[c] = from_f<T>(y);
+  }
+}
+template <typename T>
+void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int res_pitch, T* out, int out_pitch,
+                      long long npix, int C, cudaStream_t st) {
+  const int warps = 8;
+  layernorm_kernel<T><<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch, out,
+                                                                                     out_pitch, npix, C);
+}
+template void launch_layernorm<float>(const float*, int, const float*, const float*, int, float*, int, long long, int,
+                                      cudaStream_t);
+template void launch_layernorm<bf16>(const bf16*, int, const float*, const bf16*, int, bf16*, int, long long, int,
+                                     cudaStream_t);
+
+// =============================================================================================
+// LinearAttention core (module_util.py:163-177).  heads=4, dim_head=32 (fixed by the reference).
+// qkv channel layout: [q(4x32) | k(4x32) | v(4x32)], head h = channels h*32..h*32+31 of each third.
+//   pass A: per (b,h,chunk): m[d]=max_n k, s[d]=sum_n exp(k-m), c[d][e]=sum_n exp(k-m) v[e]
+//   pass B: combine chunks, ctx[d][e] = c/s/N
+//   pass C: per pixel/head: q=softmax_d(q)*32^-.5 ; out[e] = sum_d ctx[d][e] q[d]
+// =============================================================================================
+static const int LA_CH = 128;      // pixels per chunk
+static const int LA_REC = 64 + 1024;  // floats per partial record
+
+size_t linattn_partial_floats(int B, int N) { return (size_t)B * 4 * ((N + LA_CH - 1) / LA_CH) * LA_REC; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) la_partial_kernel(const T* __restrict__ qkv, int pitch, float* __restrict__ part,
+                                                         int N, int nchunks) {
+  __shared__ float ks[LA_CH][33];
+  __shared__ __align__(16) float vs[LA_CH][32];
+  __shared__ float ms[32], ss[32];
+  int chunk = blockIdx.x, bh = blockIdx.y;
+  int b = bh >> 2, h = bh & 3;
+  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int n0 = chunk * LA_CH;
+  for (int i = tid; i < LA_CH * 32; i += 256) {
+    int n = i >> 5, d = i & 31;
+    float kv = -INFINITY, vv = 0.f;
+    if (n0 + n < N) {
+      const T* row = qkv + ((long long)b * N + n0 + n) * pitch;
+      kv = to_f(row[128 + h * 32 + d]);
+      vv = to_f(row[256 + h * 32 + d]);
+    }
+    ks[n][d] = kv;
+    vs[n][d] = vv;
+  }
+  __syncthreads();
+  for (int d = warp * 4; d < warp * 4 + 4; ++d) {
+    float m = -INFINITY;
+    for (int n = lane; n < LA_CH; n += 32) m = fmaxf(m, ks[n][d]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float s = 0.f;
+    for (int n = lane; n < LA_CH; n += 32) {
+      float p = expf(ks[n][d] - m);
+      ks[n][d] = p;
+      s += p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) {
+      ms[d] = m;
+      ss[d] = s;
+    }
+  }
+  __syncthreads();
+  int d = tid >> 3, e0 = (tid & 7) * 4;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  for (int n = 0; n < LA_CH; ++n) {
+    float p = ks[n][d];
+    float4 v = *reinterpret_cast<const float4*>(&vs[n][e0]);
+    a0 += p * v.x;
+    a1 += p * v.y;
+    a2 += p * v.z;
+    a3 += p * v.w;
+  }
+  float* rec = part + ((long long)bh * nchunks + chunk) * LA_REC;
+  if (tid < 32) {
+    rec[tid] = ms[tid];
+    rec[32 + tid] = ss[tid];
+  }
+  *reinterpret_cast<float4*>(rec + 64 + d * 32 + e0) = make_float4(a0, a1, a2, a3);
+}
+
+__global__ void __launch_bounds__(1024) la_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx,
+                                                          int N, int nchunks) {
+  int bh = blockIdx.x, tid = threadIdx.x;
+  int d = tid >> 5;
+  const float* base = part + (long long)bh * nchunks * LA_REC;
+  float M = -INFINITY;
+  for (int c = 0; c < nchunks; ++c) M = fmaxf(M, base[(long long)c * LA_REC + d]);
+  float S = 0.f, acc = 0.f;
+  for (int c = 0; c < nchunks; ++c) {
+    const float* rec = base + (long long)c * LA_REC;
+    float w = expf(rec[d] - M);
+    S += rec[32 + d] * w;
+    acc += rec[64 + tid] * w;
+  }
+  ctx[(long long)bh * 1024 + tid] = acc / S / (float)N;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) la_out_kernel(const T* __restrict__ qkv, int pitch, const float* __restrict__ ctx,
+                                                     T* __restrict__ hidden, int hid_pitch, int N) {
+  __shared__ __align__(16) float cs[4][32][32];
+  int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < 4096; i += 256) (&cs[0][0][0])[i] = ctx[(long long)b * 4096 + i];
+  __syncthreads();
+  int h = tid >> 6;
+  int n = blockIdx.x * 64 + (tid & 63);
+  if (n >= N) return;
+  const T* row = qkv + ((long long)b * N + n) * pitch + h * 32;
+  float q[32];
+  float m = -INFINITY;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    q[d] = to_f(row[d]);
+    m = fmaxf(m, q[d]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+    q[d] = expf(q[d] - m);
+    s += q[d];
+  }
+  const float scale = 0.17677669529663687f;  // 32^-0.5
+#pragma unroll
+  for (int d = 0; d < 32; ++d) q[d] = q[d] / s * scale;
+  float o[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) o[e] = 0.f;
+#pragma unroll
+  for (int d = 0; d < 32; ++d) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      float4 c = *reinterpret_cast<const float4*>(&cs[h][d][e]);
+      o[e] += c.x * q[d];
+      o[e + 1] += c.y * q[d];
+      o[e + 2] += c.z * q[d];
+      o[e + 3] += c.w * q[d];
+    }
+  }
+  T* orow = hidden + ((long long)b * N + n) * hid_pitch + h * 32;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) orow[e] = from_f<T>(o[e]);
+}
+
+template <typename T>
+void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
+                    cudaStream_t st) {
+  int nchunks = (N + LA_CH - 1) / LA_CH;
+  la_partial_kernel<T><<<dim3(nchunks, B * 4), 256, 0, st>>>(qkv, qkv_pitch, partial, N, nchunks);
+  la_combine_kernel<<<B * 4, 1024, 0, st>>>(partial, ctx, N, nchunks);
+  la_out_kernel<T><<<dim3((N + 63) / 64, B), 256, 0, st>>>(qkv, qkv_pitch, ctx, hidden, hid_pitch, N);
+}
+template void launch_linattn<float>(const float*, int, float*, float*, float*, int, int, int, cudaStream_t);
+template void launch_linattn<bf16>(const bf16*, int, float*, float*, bf16*, int, int, int, cudaStream_t);
+
+// =============================================================================================
+// full softmax attention (module_util.py:192-204) - denoising-sde mid_attn only.
+// thread per query, keys/values staged through shared memory, online softmax.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) fullattn_kernel(const T* __restrict__ qkv, int pitch, T* __restrict__ hidden,
+                                                       int hid_pitch, int N) {
+  __shared__ __align__(16) float ks[64][32];
+  __shared__ __align__(16) float vs[64][32];
+  int bh = blockIdx.y, b = bh >> 2, h = bh & 3;
+  int tid = threadIdx.x;
+  int i = blockIdx.x * 128 + tid;
+  bool valid = i < N;
+  float q[32], acc[32];
+  const float scale = 0.17677669529663687f;
+  if (valid) {
+    const T* row = qkv + ((long long)b * N + i) * pitch + h * 32;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) q[d] = to_f(row[d]) * scale;
+  } else {
+#pragma unroll
+    for (int d = 0; d < 32; ++d) q[d] = 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < N; j0 += 64) {
+    __syncthreads();
+    for (int t = tid; t < 64 * 32; t += 128) {
+      int j = t >> 5, d = t & 31;
+      float kv = 0.f, vv = 0.f;
+      if (j0 + j < N) {
+        const T* row = qkv + ((long long)b * N + j0 + j) * pitch;
+        kv = to_f(row[128 + h * 32 + d]);
+        vv = to_f(row[256 + h * 32 + d]);
+      }
+      ks[j][d] = kv;
+      vs[j][d] = vv;
+    }
+    __syncthreads();
+    int jmax = min(64, N - j0);
+    for (int j = 0; j < jmax; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; d += 4) {
+        float4 k4 = *reinterpret_cast<const float4*>(&ks[j][d]);
+        s += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+      }
+      float mn = fmaxf(m, s);
+      float alpha = expf(m - mn);
+      float p = expf(s - mn);
+      l = l * alpha + p;
+#pragma unroll
+      for (int d = 0; d < 32; d += 4) {
+        float4 v4 = *reinterpret_cast<const float4*>(&vs[j][d]);
+        acc[d] = acc[d] * alpha + p * v4.x;
+        acc[d + 1] = acc[d + 1] * alpha + p * v4.y;
+        acc[d + 2] = acc[d + 2] * alpha + p * v4.z;
+        acc[d + 3] = acc[d + 3] * alpha + p * v4.w;
+      }
+      m = mn;
+    }
+  }
+  if (valid) {
+    T* orow = hidden + ((long long)b * N + i) * hid_pitch + h * 32;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) orow[d] = from_f<T>(acc[d] / l);
+  }
+}
+template <typename T>
+void launch_fullattn(const T* qkv, int qkv_pitch, T* hidden, int hid_pitch, int B, int N, cudaStream_t st) {
+  fullattn_kernel<T><<<dim3((N + 127) / 128, B * 4), 128, 0, st>>>(qkv, qkv_pitch, hidden, hid_pitch, N);
+}
+template void launch_fullattn<float>(const float*, int, float*, int, int, int, cudaStream_t);
+template void launch_fullattn<bf16>(const bf16*, int, bf16*, int, int, int, cudaStream_t);
+
+// =============================================================================================
+// timestep embedding -> per-ResBlock (scale, shift) table
+// SinusoidalPosEmb (module_util.py:29-41) -> Linear -> GELU -> Linear (DenoisingUNet_arch.py:42-47)
+// then for every ResBlock: SiLU -> Linear(4nf -> 2*Cout) (module_util.py:128-130,138-141).
+// Batch independent, so it is evaluated once per distinct t (a [rows][S] table).
+// =============================================================================================
+__global__ void time_mlp_kernel(const float* __restrict__ times, int nf, const float* __restrict__ w1,
+                                const float* __restrict__ b1, const float* __restrict__ w2,
+                                const float* __restrict__ b2, float* __restrict__ temb_silu) {
+  extern __shared__ float sm[];
+  int td = nf * 4, half = nf / 2;
+  float* emb = sm;        // [nf]
+  float* h1 = sm + nf;    // [td]
+  int row = blockIdx.x;
+  float t = times[row];
+  float e = logf(10000.0f) / (float)(half - 1);
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    float f = expf((float)i * -e);
+    float a = t * f;
+    emb[i] = sinf(a);
+    emb[half + i] = cosf(a);
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < td; o += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < nf; ++k) s += w1[o * nf + k] * emb[k];
+    s += b1[o];
+    h1[o] = 0.5f * s * (1.0f + erff(s * 0.70710678118654752440f));  // exact GELU
+  }
+  __syncthreads();
+  for (int o = threadIdx.x; o < td; o += blockDim.x) {
+    float s = 0.f;
+    for (int k = 0; k < td; ++k) s += w2[o * td + k] * h1[k];
+    s += b2[o];
+    temb_silu[(long long)row * td + o] = silu_f(s);
+  }
+}
+
+__global__ void time_table_kernel(const float* __restrict__ temb_silu, int td, const float* __restrict__ wall,
+                                  const float* __restrict__ ball, int S, float* __restrict__ table) {
+  int row = blockIdx.y;
+  int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (j >= S) return;
+  const float* w = wall + (long long)j * td;
+  const float* x = temb_silu + (long long)row * td;
+  float s = 0.f;
+  for (int k = lane; k < td; k += 32) s += w[k] * x[k];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) table[(long long)row * S + j] = s + ball[j];
+}
+
+void launch_time_table(const float* times, int rows, int nf, const float* w1, const float* b1, const float* w2,
+                       const float* b2, const float* wall, const float* ball, int S, float* temb_ws, float* table,
+                       cudaStream_t st) {
+  int td = nf * 4;
+  time_mlp_kernel<<<rows, 256, (nf + td) * sizeof(float), st>>>(times, nf, w1, b1, w2, b2, temb_ws);
+  time_table_kernel<<<dim3((S + 7) / 8, rows), 256, 0, st>>>(temb_ws, td, wall, ball, S, table);
+}
+
+// =============================================================================================
+// sampler update (one fused kernel per step).  Op order follows the reference exactly, with
+// explicit round-to-nearest intrinsics so ptxas cannot contract to FMA:
+//   sde_utils.py:44-48,175-185 (IRSDE sde/ode), :197-223,237-239 (posterior),
+//   :450-462 (DenoisingSDE).
+// coef row layout (IRSDE_NUM_COEF floats per t), see engine.cu fill_default_coeffs():
+//   SDE      : theta, sigma^2, sigma_bar, dt, sigma, sqrt(dt)
+//   ODE      : theta, 0.5*sigma^2, sigma_bar, dt
+//   POSTERIOR: exp(Theta_t dt), sigma_bar, term1, term2, std
+//   DSDE_SDE : -0.5 sigma^2 (1+A), sigma_bar, dt, sigma, sqrt(dt)
+//   DSDE_ODE : -0.5 sigma^2 A, sigma_bar, dt
+// =============================================================================================
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
+  unsigned long long p = (unsigned long long)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    uint32_t lo0 = mulhilo(0xD2511F53u, c[0], &hi0);
+    uint32_t lo1 = mulhilo(0xCD9E8D57u, c[2], &hi1);
+    uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0;
+    c[1] = n1;
+    c[2] = n2;
+    c[3] = n3;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ void normal4(uint64_t seed, uint64_t ctr, uint32_t stream, float out[4]) {
+  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), stream, 0x1234567u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float two_pow_m32 = 2.3283064365386963e-10f;
+  float u0 = ((float)c[0] + 0.5f) * two_pow_m32, u1 = ((float)c[1] + 0.5f) * two_pow_m32;
+  float u2 = ((float)c[2] + 0.5f) * two_pow_m32, u3 = ((float)c[3] + 0.5f) * two_pow_m32;
+  u0 = fminf(fmaxf(u0, 1e-12f), 1.0f);
+  u2 = fminf(fmaxf(u2, 1e-12f), 1.0f);
+  float r0 = sqrtf(-2.0f * logf(u0)), r1 = sqrtf(-2.0f * logf(u2));
+  float s0, c0, s1, c1;
+  sincosf(6.283185307179586f * u1, &s0, &c0);
+  sincosf(6.283185307179586f * u3, &s1, &c1);
+  out[0] = r0 * c0;
+  out[1] = r0 * s0;
+  out[2] = r1 * c1;
+  out[3] = r1 * s1;
+}
+
+__device__ __forceinline__ float sde_update_one(int mode, const float* c, float x, float mu, float eps, float z) {
+  switch (mode) {
+    case 0: {  // IRSDE sde
+      float score = __fdiv_rn(-eps, c[2]);
+      float drift = __fmul_rn(__fsub_rn(__fmul_rn(c[0], __fsub_rn(mu, x)), __fmul_rn(c[1], score)), c[3]);
+      float disp = __fmul_rn(c[4], __fmul_rn(z, c[5]));
+      return __fsub_rn(__fsub_rn(x, drift), disp);
+    }
+    case 1: {  // IRSDE ode
+      float score = __fdiv_rn(-eps, c[2]);
+      float drift = __fmul_rn(__fsub_rn(__fmul_rn(c[0], __fsub_rn(mu, x)), __fmul_rn(c[1], score)), c[3]);
+      return __fsub_rn(x, drift);
+    }
+    case 2: {  // IRSDE posterior
+      float xm = __fsub_rn(x, mu);
+      float x0 = __fadd_rn(__fmul_rn(__fsub_rn(xm, __fmul_rn(c[1], eps)), c[0]), mu);
+      float mean = __fadd_rn(__fadd_rn(__fmul_rn(c[2], xm), __fmul_rn(c[3], __fsub_rn(x0, mu))), mu);
+      return __fadd_rn(mean, __fmul_rn(c[4], z));
+    }
+    case 3: {  // DenoisingSDE sde
+      float score = __fdiv_rn(-eps, c[1]);
+      float drift = __fmul_rn(__fmul_rn(c[0], score), c[2]);
+      float disp = __fmul_rn(c[3], __fmul_rn(z, c[4]));
+      return __fsub_rn(__fsub_rn(x, drift), disp);
+    }
+    default: {  // DenoisingSDE ode
+      float score = __fdiv_rn(-eps, c[1]);
+      float drift = __fmul_rn(__fmul_rn(c[0], score), c[2]);
+      return __fsub_rn(x, drift);
+    }
+  }
+}
+
+__global__ void sde_update_kernel(int mode, const float* __restrict__ x, const float* __restrict__ mu,
+                                  const float* __restrict__ noise, const float* __restrict__ z, long long z_stride,
+                                  const float* __restrict__ coef, const StepState* __restrict__ stp, int t_host,
+                                  float* __restrict__ out, long long n, uint64_t seed) {
+  int t = stp ? stp->t : t_host;
+  int si = stp ? stp->i : 0;
+  float c[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) c[k] = coef[t * 8 + k];
+  bool need_z = (mode == 0 || mode == 2 || mode == 3);
+  if (stp) { z = stp->z; seed = stp->seed; }
+  const float* zz = z ? z + (long long)si * z_stride : nullptr;
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
+  long long i0 = q * 4;
+  if (i0 >= n) return;
+  float zr[4] = {0.f, 0.f, 0.f, 0.f};
+  if (need_z && !zz) normal4(seed, (uint64_t)q, (uint32_t)t, zr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    long long i = i0 + k;
+    if (i < n) {
+      float zv = need_z ? (zz ? zz[i] : zr[k]) : 0.f;
+      float mv = mu ? mu[i] : 0.f;
+      out[i] = sde_update_one(mode, c, x[i], mv, noise[i], zv);
+    }
+  }
+}
+
+void launch_sde_update(int mode, const float* x, const float* mu, const float* noise, const float* z, long long z_stride,
+                       const float* coef, const StepState* st_dev, int t_host, float* out, long long n, uint64_t seed,
+                       cudaStream_t st) {
+  long long groups = (n + 3) / 4;
+  sde_update_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(mode, x, mu, noise, z, z_stride, coef, st_dev,
+                                                                      t_host, out, n, seed);
+}
+
+__global__ void advance_step_kernel(StepState* s) {
+  s->t -= 1;
+  s->i += 1;
+}
+__global__ void set_step_kernel(StepState* s, int t, int i, const float* z, unsigned long long seed) {
+  s->t = t;
+  s->i = i;
+  s->z = z;
+  s->seed = seed;
+}
+void launch_advance_step(StepState* st_dev, cudaStream_t st) { advance_step_kernel<<<1, 1, 0, st>>>(st_dev); }
+void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned long long seed, cudaStream_t st) {
+  set_step_kernel<<<1, 1, 0, st>>>(st_dev, t, i, z, seed);
+}
+
+__global__ void noise_state_kernel(const float* __restrict__ mu, float* __restrict__ out, long long n, float max_sigma,
+                                   uint64_t seed) {
+  long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long i0 = q * 4;
+  if (i0 >= n) return;
+  float zr[4];
+  normal4(seed, (uint64_t)q, 0xffffffffu, zr);
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    if (i0 + k < n) out[i0 + k] = mu[i0 + k] + zr[k] * max_sigma;
+}
+void launch_noise_state(const float* mu, float* out, long long n, float max_sigma, uint64_t seed, cudaStream_t st) {
+  long long groups = (n + 3) / 4;
+  noise_state_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(mu, out, n, max_sigma, seed);
+}
+
+// =============================================================================================
+// space-to-depth (stride-2 phase planes) for the 4x4/s2 downsample on the tensor-core path:
+// out[plane=(h&1)*2+(w&1)][b][h/2][w/2][c] = in[b][h][w][c]
+// =============================================================================================
+template <typename T>
+__global__ void s2d_kernel(const T* __restrict__ in, int pitch, T* __restrict__ out, int B, int H, int W, int C) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W*(C/8) 16-byte groups
+  int vec = 16 / sizeof(T);
+  int cg = C / vec;
+  long long total = (long long)B * H * W * cg;
+  if (idx >= total) return;
+  int g = idx % cg;
+  long long pix = idx / cg;
+  int w = pix % W;
+  int h = (pix / W) % H;
+  int b = pix / ((long long)W * H);
+  int plane = (h & 1) * 2 + (w & 1);
+  long long o = ((((long long)plane * B + b) * (H / 2) + (h >> 1)) * (W / 2) + (w >> 1)) * C + g * vec;
+  *reinterpret_cast<uint4*>(out + o) = *reinterpret_cast<const uint4*>(in + pix * pitch + g * vec);
+}
+template <typename T>
+void launch_space_to_depth(const T* in, int in_pitch, T* out, int B, int H, int W, int C, cudaStream_t st) {
+  int vec = 16 / sizeof(T);
+  long long total = (long long)B * H * W * (C / vec);
+  s2d_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, in_pitch, out, B, H, W, C);
+}
+template void launch_space_to_depth<bf16>(const bf16*, int, bf16*, int, int, int, int, cudaStream_t);
+template void launch_space_to_depth<float>(const float*, int, float*, int, int, int, int, cudaStream_t);
+
+}  // namespace irsde

@@ -1,0 +1,998 @@
+// irsde_b200 engine: context, weight store/repack, ConditionalUNet launch plan, sampler chain
+// (CUDA-graph replay of one captured step) and the C ABI declared in include/irsde_b200.h.
+//
+// Data layout in HBM: activations are NHWC (channels-last) so that the skip concatenations of the
+// UNet (DenoisingUNet_arch.py:118,121,127) are channel-offset views into one pre-allocated buffer
+// (producers write at their channel offset: no torch.cat copies) and so that a 64-channel slab of a
+// pixel row is one 128-byte line (the TMA / UMMA swizzle atom of the tensor-core engine).
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <string>
+#include <tuple>
+#include <type_traits>
+#include <vector>
+
+#include "../../include/irsde_b200.h"
+#include "common.cuh"
+
+using namespace irsde;
+
+namespace {
+thread_local std::string g_last_error;
+
+struct RawTensor {
+  std::vector<int64_t> shape;
+  float* dev = nullptr;
+  long long numel = 0;
+};
+
+struct RunCfg {  // per-invocation pointers read by the op closures at launch time
+  const float* x = nullptr;
+  const float* mu = nullptr;
+  float* out = nullptr;
+  const float* ss = nullptr;  // time-modulation table
+  const int* t_ptr = nullptr;
+  int ss_img_stride = 0;
+};
+
+struct Plan;
+typedef std::function<void(Plan*, cudaStream_t)> Op;
+
+struct Plan {
+  int B, H, W, Hp, Wp;
+  std::vector<void*> allocs;
+  std::vector<Op> ops;
+  std::vector<TcConvDesc*> tc_descs;
+  RunCfg cur;
+  // chain state
+  float *x_state = nullptr, *mu_buf = nullptr, *eps_buf = nullptr;
+  StepState* d_step = nullptr;
+  int* d_zero = nullptr;
+  float *fwd_times = nullptr, *fwd_temb = nullptr, *fwd_table = nullptr;        // module-forward table (B rows)
+  float *chain_times = nullptr, *chain_temb = nullptr, *chain_table = nullptr;  // chain table rows 0..cap-1
+  int chain_cap = 0;
+  cudaGraphExec_t graph[IRSDE_NUM_MODES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  long long step_launches[IRSDE_NUM_MODES] = {0, 0, 0, 0, 0};
+};
+}  // namespace
+
+struct irsde_ctx {
+  irsde_config cfg;
+  mutable std::string err;
+  std::map<std::string, RawTensor> raw;
+  bool finalized = false;
+  std::map<std::string, float*> w_simt;  // [KH*KW][Cin][Cout] fp32
+  std::map<std::string, bf16*> w_tc;     // [phase][tap][Cout][Cin] bf16
+  std::map<std::string, int> ss_off;
+  float *wall = nullptr, *ball = nullptr;
+  int S = 0;
+  // schedule
+  bool have_sched = false;
+  int T = 0;
+  float dt = 0, max_sigma = 0;
+  std::vector<float> thetas, sigmas, cumsum, sbars;
+  float* coef_dev[IRSDE_NUM_MODES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  std::map<std::tuple<int, int, int>, Plan*> plans;
+  long long launches = 0;
+  long long dev_bytes = 0;
+  std::vector<void*> allocs;
+  bool tc_ok = false;
+  bool use_tc = false;  // bf16 mode: route eligible convs through the tcgen05 engine
+};
+
+namespace {
+
+#define CUDA_TRY(ctx, expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) {                                                                     \
+      char _b[512];                                                                              \
+      snprintf(_b, sizeof(_b), "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      (ctx)->err = _b;                                                                           \
+      g_last_error = _b;                                                                         \
+      return IRSDE_ERR_CUDA;                                                                     \
+    }                                                                                            \
+  } while (0)
+
+int fail(const irsde_ctx* ctx, int code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  g_last_error = msg;
+  return code;
+}
+
+void* dev_alloc(irsde_ctx* ctx, size_t bytes, std::vector<void*>* owner) {
+  void* p = nullptr;
+  if (bytes == 0) bytes = 16;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+  ctx->dev_bytes += (long long)bytes;
+  owner->push_back(p);
+  return p;
+}
+
+// ---- weight repack kernels ---------------------------------------------------------------------
+__global__ void pack_simt_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cin, int KH, int KW) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Cout * Cin * KH * KW;
+  if (idx >= total) return;
+  int co = idx % Cout;
+  int c = (idx / Cout) % Cin;
+  int tap = idx / ((long long)Cout * Cin);
+  int r = tap / KW, s = tap % KW;
+  o[idx] = w[(((long long)co * Cin + c) * KH + r) * KW + s];
+}
+// [tap][Cout][Cin] bf16
+__global__ void pack_tc_kernel(const float* __restrict__ w, bf16* __restrict__ o, int Cout, int Cin, int KH, int KW) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Cout * Cin * KH * KW;
+  if (idx >= total) return;
+  int c = idx % Cin;
+  int co = (idx / Cin) % Cout;
+  int tap = idx / ((long long)Cout * Cin);
+  int r = tap / KW, s = tap % KW;
+  o[idx] = __float2bfloat16_rn(w[(((long long)co * Cin + c) * KH + r) * KW + s]);
+}
+// nearest-x2 upsample followed by 3x3/pad1 == four 2x2 phase convolutions on the low-res input with
+// pre-summed weights: [phase=(py,px)][tap=(a,b)][Cout][Cin]
+__global__ void pack_tc_up_kernel(const float* __restrict__ w, bf16* __restrict__ o, int Cout, int Cin) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)16 * Cout * Cin;
+  if (idx >= total) return;
+  int c = idx % Cin;
+  int co = (idx / Cin) % Cout;
+  int tap = (idx / ((long long)Cout * Cin)) % 4;
+  int phase = idx / ((long long)4 * Cout * Cin);
+  int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+  // rows of the 3x3 kernel that fall on low-res offset a for phase py
+  int r0, r1, s0, s1;
+  if (py == 0) { if (a == 0) { r0 = 0; r1 = 0; } else { r0 = 1; r1 = 2; } }
+  else         { if (a == 0) { r0 = 0; r1 = 1; } else { r0 = 2; r1 = 2; } }
+  if (px == 0) { if (b == 0) { s0 = 0; s1 = 0; } else { s0 = 1; s1 = 2; } }
+  else         { if (b == 0) { s0 = 0; s1 = 1; } else { s0 = 2; s1 = 2; } }
+  float acc = 0.f;
+  for (int r = r0; r <= r1; ++r)
+    for (int s = s0; s <= s1; ++s) acc += w[(((long long)co * Cin + c) * 3 + r) * 3 + s];
+  o[idx] = __float2bfloat16_rn(acc);
+}
+
+// ---- architecture description --------------------------------------------------------------------
+struct ResBlockInfo {
+  std::string pre;
+  int cin, cout;
+};
+std::vector<ResBlockInfo> resblocks(const irsde_config& c) {
+  std::vector<ResBlockInfo> v;
+  char b[64];
+  for (int i = 0; i < c.depth; ++i) {
+    int di = c.nf << i;
+    snprintf(b, sizeof b, "downs.%d.0.", i); v.push_back({b, di, di});
+    snprintf(b, sizeof b, "downs.%d.1.", i); v.push_back({b, di, di});
+  }
+  int mid = c.nf << c.depth;
+  v.push_back({"mid_block1.", mid, mid});
+  v.push_back({"mid_block2.", mid, mid});
+  for (int j = 0; j < c.depth; ++j) {
+    int i = c.depth - 1 - j, di = c.nf << i, dout = c.nf << (i + 1);
+    snprintf(b, sizeof b, "ups.%d.0.", j); v.push_back({b, dout + di, dout});
+    snprintf(b, sizeof b, "ups.%d.1.", j); v.push_back({b, dout + di, dout});
+  }
+  v.push_back({"final_res_block.", 2 * c.nf, c.nf});
+  return v;
+}
+
+struct ParamSpec {
+  std::string name;
+  std::vector<int64_t> shape;
+};
+std::vector<ParamSpec> param_specs(const irsde_config& c) {
+  std::vector<ParamSpec> v;
+  int64_t nf = c.nf, td = 4 * nf;
+  int64_t cin0 = c.variant == IRSDE_NET_CONDITIONAL ? 2 * c.in_nc : c.in_nc;
+  v.push_back({"init_conv.weight", {nf, cin0, 7, 7}});
+  v.push_back({"time_mlp.1.weight", {td, nf}});
+  v.push_back({"time_mlp.1.bias", {td}});
+  v.push_back({"time_mlp.3.weight", {td, td}});
+  v.push_back({"time_mlp.3.bias", {td}});
+  for (auto& rb : resblocks(c)) {
+    v.push_back({rb.pre + "mlp.1.weight", {2 * rb.cout, td}});
+    v.push_back({rb.pre + "mlp.1.bias", {2 * rb.cout}});
+    v.push_back({rb.pre + "block1.proj.weight", {rb.cout, rb.cin, 3, 3}});
+    v.push_back({rb.pre + "block2.proj.weight", {rb.cout, rb.cout, 3, 3}});
+    if (rb.cin != rb.cout) v.push_back({rb.pre + "res_conv.weight", {rb.cout, rb.cin, 1, 1}});
+  }
+  auto attn = [&](const std::string& pre, int64_t C, bool full) {
+    v.push_back({pre + "fn.fn.to_qkv.weight", {384, C, 1, 1}});
+    if (full) {
+      v.push_back({pre + "fn.fn.to_out.weight", {C, 128, 1, 1}});
+      v.push_back({pre + "fn.fn.to_out.bias", {C}});
+    } else {
+      v.push_back({pre + "fn.fn.to_out.0.weight", {C, 128, 1, 1}});
+      v.push_back({pre + "fn.fn.to_out.0.bias", {C}});
+      v.push_back({pre + "fn.fn.to_out.1.g", {1, C, 1, 1}});
+    }
+    v.push_back({pre + "fn.norm.g", {1, C, 1, 1}});
+  };
+  char b[64];
+  for (int i = 0; i < c.depth; ++i) {
+    int64_t di = nf << i, dout = nf << (i + 1);
+    snprintf(b, sizeof b, "downs.%d.2.", i);
+    attn(b, di, false);
+    snprintf(b, sizeof b, "downs.%d.3.", i);
+    if (i != c.depth - 1) {
+      v.push_back({std::string(b) + "weight", {dout, di, 4, 4}});
+      v.push_back({std::string(b) + "bias", {dout}});
+    } else {
+      v.push_back({std::string(b) + "weight", {dout, di, 3, 3}});
+    }
+  }
+  attn("mid_attn.", nf << c.depth, c.variant == IRSDE_NET_DENOISING);
+  for (int j = 0; j < c.depth; ++j) {
+    int i = c.depth - 1 - j;
+    int64_t di = nf << i, dout = nf << (i + 1);
+    snprintf(b, sizeof b, "ups.%d.2.", j);
+    attn(b, dout, false);
+    if (i != 0) {
+      snprintf(b, sizeof b, "ups.%d.3.1.", j);
+      v.push_back({std::string(b) + "weight", {di, dout, 3, 3}});
+      v.push_back({std::string(b) + "bias", {di}});
+    } else {
+      snprintf(b, sizeof b, "ups.%d.3.", j);
+      v.push_back({std::string(b) + "weight", {di, dout, 3, 3}});
+    }
+  }
+  v.push_back({"final_conv.weight", {c.out_nc, nf, 3, 3}});
+  v.push_back({"final_conv.bias", {c.out_nc}});
+  return v;
+}
+
+// ---- plan builder ----------------------------------------------------------------------------------
+template <typename T>
+struct Builder {
+  irsde_ctx* ctx;
+  Plan* plan;
+  bool ok = true;
+  std::string err;
+  std::multimap<size_t, void*> free_tmp;
+  std::map<void*, size_t> tmp_size;
+
+  T* alloc(long long elems) {
+    void* p = dev_alloc(ctx, (size_t)elems * sizeof(T), &plan->allocs);
+    if (!p) { ok = false; err = "cudaMalloc failed in plan builder"; }
+    return (T*)p;
+  }
+  T* tmp(long long elems) {
+    size_t bytes = (size_t)elems * sizeof(T);
+    auto it = free_tmp.lower_bound(bytes);
+    if (it != free_tmp.end() && it->first <= bytes * 2 + 4096) {
+      void* p = it->second;
+      free_tmp.erase(it);
+      return (T*)p;
+    }
+    void* p = alloc(elems);
+    tmp_size[p] = bytes;
+    return (T*)p;
+  }
+  void release(void* p) { free_tmp.insert({tmp_size[p], p}); }
+
+  float* fw(const std::string& n) {  // fp32 raw parameter (bias / gain vectors)
+    auto it = ctx->raw.find(n);
+    if (it == ctx->raw.end()) { ok = false; err = "missing tensor " + n; return nullptr; }
+    return it->second.dev;
+  }
+
+  struct V { T* p; int pitch; int C; };  // channel-offset NHWC view
+  static V view(T* base, int pitch, int off, int C) { return V{base + off, pitch, C}; }
+
+  // generic conv op. ss_block = ResBlock prefix whose (scale,shift) modulate the output ("" = none)
+  void conv(const std::string& wname, V in, int Hin, int Win, int K, int stride, int pad, int up, const char* bias,
+            const std::string& ss_block, int silu, const V* res, V out, int Cout, float** out_nchw_slot = nullptr) {
+    ConvGeom g;
+    g.B = plan->B; g.Hin = Hin; g.Win = Win; g.Cin = in.C; g.up = up; g.KH = K; g.KW = K; g.stride = stride; g.pad = pad;
+    g.Hout = (Hin * up + 2 * pad - K) / stride + 1;
+    g.Wout = (Win * up + 2 * pad - K) / stride + 1;
+    g.Cout = Cout;
+    Epilogue ep;
+    memset(&ep, 0, sizeof ep);
+    ep.bias = bias ? fw(bias) : nullptr;
+    ep.silu = silu;
+    ep.ss_S = ctx->S;
+    bool use_ss = !ss_block.empty();
+    ep.ss_off = use_ss ? ctx->ss_off[ss_block] : 0;
+    if (res) { ep.res = res->p; ep.res_pitch = res->pitch; }
+    irsde_ctx* c = ctx;
+    bool nchw = out_nchw_slot != nullptr;
+    if constexpr (std::is_same<T, bf16>::value) {
+      bool shape_ok = (K == 3 && stride == 1 && pad == 1) || (K == 1 && stride == 1 && pad == 0 && up == 1) ||
+                      (K == 4 && stride == 2 && pad == 1 && up == 1 && Hin % 2 == 0 && Win % 2 == 0);
+      if (ctx->use_tc && !nchw && shape_ok && in.C % 8 == 0 && Cout % 8 == 0 && in.pitch % 8 == 0 && out.pitch % 8 == 0) {
+        const bf16* wt = ctx->w_tc[wname];
+        if (!wt) { ok = false; err = "unpacked tc weight " + wname; return; }
+        TcTap taps[16];
+        int ntaps = 0, nph = 1, planes = 1, Ha = Hin, Wa = Win, a_pitch = in.pitch;
+        const bf16* a_ptr = in.p;
+        if (K == 3 && up == 1) {
+          for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) taps[ntaps++] = TcTap{r - 1, q - 1, 0};
+        } else if (K == 3 && up == 2) {
+          nph = 4;
+          for (int a = 0; a < 2; ++a) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{a - 1, q - 1, 0};
+        } else if (K == 1) {
+          taps[ntaps++] = TcTap{0, 0, 0};
+        } else {  // 4x4 stride 2 pad 1 over space-to-depth planes
+          static const int PY[4] = {1, 0, 1, 0}, DH[4] = {-1, 0, 0, 1};
+          for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) taps[ntaps++] = TcTap{DH[r], DH[q], PY[r] * 2 + PY[q]};
+          planes = 4; Ha = Hin / 2; Wa = Win / 2; a_pitch = in.C;
+          bf16* s2d = tmp((long long)plan->B * Hin * Win * in.C);
+          int Bc = plan->B, Cc = in.C;
+          plan->ops.push_back([=](Plan*, cudaStream_t st) {
+            launch_space_to_depth<bf16>(in.p, in.pitch, s2d, Bc, Hin, Win, Cc, st);
+            c->launches++;
+          });
+          a_ptr = s2d;
+          release(s2d);  // safe: stream order; the next tmp user runs after this conv
+        }
+        std::string terr;
+        TcConvDesc* d = tc_conv_create(a_ptr, a_pitch, plan->B, Ha, Wa, in.C, planes, wt, Cout, ntaps, taps, nph, ep, out.p,
+                                       out.pitch, g.Hout, g.Wout, &terr);
+        if (!d) { ok = false; err = "tc_conv_create(" + wname + "): " + terr; return; }
+        plan->tc_descs.push_back(d);
+        plan->ops.push_back([=](Plan* p, cudaStream_t st) {
+          if (use_ss) tc_conv_set_runtime(d, p->cur.ss, p->cur.t_ptr, p->cur.ss_img_stride);
+          tc_conv_launch(d, st);
+          c->launches++;
+        });
+        return;
+      }
+    }
+    const float* w = ctx->w_simt[wname];
+    if (!w) { ok = false; err = "unpacked weight " + wname; return; }
+    int H = plan->H, Wd = plan->W;
+    plan->ops.push_back([=](Plan* p, cudaStream_t st) {
+      Epilogue e = ep;
+      if (use_ss) { e.ss = p->cur.ss; e.t_ptr = p->cur.t_ptr; e.ss_img_stride = p->cur.ss_img_stride; }
+      launch_conv_simt<T>(g, in.p, in.pitch, w, e, out.p, out.pitch, nchw ? p->cur.out : nullptr, H, Wd, st);
+      c->launches++;
+    });
+  }
+
+  void resblock(const std::string& pre, V in, int Cout, V out, int H, int W) {
+    long long npix = (long long)plan->B * H * W;
+    T* h1 = tmp(npix * Cout);
+    V vh1{h1, Cout, Cout};
+    conv(pre + "block1.proj.weight", in, H, W, 3, 1, 1, 1, nullptr, pre, 1, nullptr, vh1, Cout);
+    V res = in;
+    T* r = nullptr;
+    if (in.C != Cout) {
+      r = tmp(npix * Cout);
+      res = V{r, Cout, Cout};
+      conv(pre + "res_conv.weight", in, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, res, Cout);
+    }
+    conv(pre + "block2.proj.weight", vh1, H, W, 3, 1, 1, 1, nullptr, "", 1, &res, out, Cout);
+    release(h1);
+    if (r) release(r);
+  }
+
+  // Residual(PreNorm(LinearAttention)) or Residual(PreNorm(Attention)); pre = "...2." / "mid_attn."
+  void attention(const std::string& pre, V in, V out, int H, int W, bool full, float* la_partial, float* la_ctx) {
+    int C = in.C, B = plan->B, N = H * W;
+    long long npix = (long long)B * N;
+    T* xn = tmp(npix * C);
+    float* g1 = fw(pre + "fn.norm.g");
+    irsde_ctx* c = ctx;
+    plan->ops.push_back([=](Plan*, cudaStream_t st) {
+      launch_layernorm<T>(in.p, in.pitch, g1, nullptr, 0, xn, C, npix, C, st);
+      c->launches++;
+    });
+    T* qkv = tmp(npix * 384);
+    conv(pre + "fn.fn.to_qkv.weight", V{xn, C, C}, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384);
+    release(xn);
+    T* hid = tmp(npix * 128);
+    if (full) {
+      plan->ops.push_back([=](Plan*, cudaStream_t st) {
+        launch_fullattn<T>(qkv, 384, hid, 128, B, N, st);
+        c->launches++;
+      });
+      std::string bn = pre + "fn.fn.to_out.bias";
+      conv(pre + "fn.fn.to_out.weight", V{hid, 128, 128}, H, W, 1, 1, 0, 1, bn.c_str(), "", 0, &in, out, C);
+    } else {
+      plan->ops.push_back([=](Plan*, cudaStream_t st) {
+        launch_linattn<T>(qkv, 384, la_partial, la_ctx, hid, 128, B, N, st);
+        c->launches += 3;
+      });
+      T* y = tmp(npix * C);
+      std::string bn = pre + "fn.fn.to_out.0.bias";
+      conv(pre + "fn.fn.to_out.0.weight", V{hid, 128, 128}, H, W, 1, 1, 0, 1, bn.c_str(), "", 0, nullptr, V{y, C, C}, C);
+      float* g2 = fw(pre + "fn.fn.to_out.1.g");
+      plan->ops.push_back([=](Plan*, cudaStream_t st) {
+        launch_layernorm<T>(y, C, g2, in.p, in.pitch, out.p, out.pitch, npix, C, st);
+        c->launches++;
+      });
+      release(y);
+    }
+    release(qkv);
+    release(hid);
+  }
+
+  void build() {
+    const irsde_config& c = ctx->cfg;
+    int B = plan->B, nf = c.nf, depth = c.depth;
+    int s = 1 << depth;
+    plan->Hp = plan->H + (s - plan->H % s) % s;
+    plan->Wp = plan->W + (s - plan->W % s) % s;
+    std::vector<int> hs(depth), ws(depth);
+    hs[0] = plan->Hp; ws[0] = plan->Wp;
+    for (int i = 1; i < depth; ++i) { hs[i] = hs[i - 1] / 2; ws[i] = ws[i - 1] / 2; }
+    bool cond = c.variant == IRSDE_NET_CONDITIONAL;
+    int C0 = cond ? 2 * c.in_nc : c.in_nc;
+    int pitch0 = (C0 + 7) / 8 * 8;
+    long long np0 = (long long)B * hs[0] * ws[0];
+    // linear-attention scratch sized for the largest level
+    float* la_partial = (float*)dev_alloc(ctx, linattn_partial_floats(B, hs[0] * ws[0]) * sizeof(float), &plan->allocs);
+    float* la_ctx = (float*)dev_alloc(ctx, (size_t)B * 4096 * sizeof(float), &plan->allocs);
+    if (!la_partial || !la_ctx) { ok = false; err = "cudaMalloc failed"; return; }
+
+    T* X0 = alloc(np0 * pitch0);
+    T* F = alloc(np0 * 2 * nf);
+    int in_nc = c.in_nc, Hh = plan->H, Ww = plan->W, Hp = plan->Hp, Wp = plan->Wp;
+    irsde_ctx* cx = ctx;
+    plan->ops.push_back([=](Plan* p, cudaStream_t st) {
+      launch_prep_input<T>(p->cur.x, p->cur.mu, X0, B, in_nc, Hh, Ww, Hp, Wp, pitch0, cond ? 1 : 0, st);
+      cx->launches++;
+    });
+    conv("init_conv.weight", V{X0, pitch0, C0}, hs[0], ws[0], 7, 1, 3, 1, nullptr, "", 0, nullptr, view(F, 2 * nf, nf, nf), nf);
+    V cur = view(F, 2 * nf, nf, nf);
+    std::vector<T*> U1(depth), U2(depth);
+    char nb[64];
+    for (int i = 0; i < depth; ++i) {
+      int di = nf << i, dout = nf << (i + 1), H = hs[i], W = ws[i];
+      long long npix = (long long)B * H * W;
+      U1[i] = alloc(npix * (dout + di));
+      U2[i] = alloc(npix * (dout + di));
+      snprintf(nb, sizeof nb, "downs.%d.", i);
+      std::string pre = nb;
+      V s2 = view(U2[i], dout + di, dout, di), s1 = view(U1[i], dout + di, dout, di);
+      resblock(pre + "0.", cur, di, s2, H, W);
+      T* ta = tmp(npix * di);
+      resblock(pre + "1.", s2, di, V{ta, di, di}, H, W);
+      attention(pre + "2.", V{ta, di, di}, s1, H, W, false, la_partial, la_ctx);
+      release(ta);
+      if (i != depth - 1) {
+        T* xn = alloc((long long)B * hs[i + 1] * ws[i + 1] * dout);
+        std::string bn = pre + "3.bias";
+        conv(pre + "3.weight", s1, H, W, 4, 2, 1, 1, bn.c_str(), "", 0, nullptr, V{xn, dout, dout}, dout);
+        cur = V{xn, dout, dout};
+      } else {
+        T* xn = alloc(npix * dout);
+        conv(pre + "3.weight", s1, H, W, 3, 1, 1, 1, nullptr, "", 0, nullptr, V{xn, dout, dout}, dout);
+        cur = V{xn, dout, dout};
+      }
+    }
+    {
+      int i = depth - 1, di = nf << i, mid = nf << depth, H = hs[i], W = ws[i];
+      long long npix = (long long)B * H * W;
+      T* m1 = tmp(npix * mid);
+      T* m2 = tmp(npix * mid);
+      resblock("mid_block1.", cur, mid, V{m1, mid, mid}, H, W);
+      attention("mid_attn.", V{m1, mid, mid}, V{m2, mid, mid}, H, W, c.variant == IRSDE_NET_DENOISING, la_partial, la_ctx);
+      resblock("mid_block2.", V{m2, mid, mid}, mid, view(U1[i], mid + di, 0, mid), H, W);
+      release(m1);
+      release(m2);
+    }
+    for (int j = 0; j < depth; ++j) {
+      int i = depth - 1 - j, di = nf << i, dout = nf << (i + 1), H = hs[i], W = ws[i];
+      long long npix = (long long)B * H * W;
+      snprintf(nb, sizeof nb, "ups.%d.", j);
+      std::string pre = nb;
+      resblock(pre + "0.", V{U1[i], dout + di, dout + di}, dout, view(U2[i], dout + di, 0, dout), H, W);
+      T* tb = tmp(npix * dout);
+      resblock(pre + "1.", V{U2[i], dout + di, dout + di}, dout, V{tb, dout, dout}, H, W);
+      T* tc = tmp(npix * dout);
+      attention(pre + "2.", V{tb, dout, dout}, V{tc, dout, dout}, H, W, false, la_partial, la_ctx);
+      release(tb);
+      if (i != 0) {
+        int dprev = nf << i;  // == dout of level i-1
+        std::string bn = pre + "3.1.bias";
+        conv(pre + "3.1.weight", V{tc, dout, dout}, H, W, 3, 1, 1, 2, bn.c_str(), "", 0, nullptr,
+             view(U1[i - 1], dprev + (nf << (i - 1)), 0, dprev), di);
+      } else {
+        conv(pre + "3.weight", V{tc, dout, dout}, H, W, 3, 1, 1, 1, nullptr, "", 0, nullptr, view(F, 2 * nf, 0, nf), di);
+      }
+      release(tc);
+    }
+    T* G = tmp(np0 * nf);
+    resblock("final_res_block.", V{F, 2 * nf, 2 * nf}, nf, V{G, nf, nf}, hs[0], ws[0]);
+    float* dummy = nullptr;
+    conv("final_conv.weight", V{G, nf, nf}, hs[0], ws[0], 3, 1, 1, 1, "final_conv.bias", "", 0, nullptr, V{nullptr, 0, 0},
+         c.out_nc, &dummy);
+  }
+};
+
+int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
+  auto key = std::make_tuple(B, H, W);
+  auto it = ctx->plans.find(key);
+  if (it != ctx->plans.end()) { *out = it->second; return IRSDE_OK; }
+  if (B <= 0 || H <= 0 || W <= 0) return fail(ctx, IRSDE_ERR_INVALID, "bad image shape");
+  int s = 1 << ctx->cfg.depth;
+  // reflect pad needs pad < size (F.pad 'reflect' raises otherwise, DenoisingUNet_arch.py:82)
+  if ((s - H % s) % s >= H || (s - W % s) % s >= W) return fail(ctx, IRSDE_ERR_INVALID, "image too small for reflect padding");
+  Plan* p = new Plan();
+  p->B = B; p->H = H; p->W = W;
+  std::string err;
+  bool ok;
+  if (ctx->cfg.precision == IRSDE_PREC_FP32) {
+    Builder<float> b{ctx, p};
+    b.build();
+    ok = b.ok; err = b.err;
+  } else {
+    Builder<bf16> b{ctx, p};
+    b.build();
+    ok = b.ok; err = b.err;
+  }
+  long long n = (long long)B * ctx->cfg.in_nc * H * W;
+  long long no = (long long)B * ctx->cfg.out_nc * H * W;
+  p->x_state = (float*)dev_alloc(ctx, n * 4, &p->allocs);
+  p->mu_buf = (float*)dev_alloc(ctx, n * 4, &p->allocs);
+  p->eps_buf = (float*)dev_alloc(ctx, no * 4, &p->allocs);
+  p->d_step = (StepState*)dev_alloc(ctx, sizeof(StepState), &p->allocs);
+  p->d_zero = (int*)dev_alloc(ctx, sizeof(int), &p->allocs);
+  int td = ctx->cfg.nf * 4;
+  p->fwd_times = (float*)dev_alloc(ctx, (size_t)B * 4, &p->allocs);
+  p->fwd_temb = (float*)dev_alloc(ctx, (size_t)B * td * 4, &p->allocs);
+  p->fwd_table = (float*)dev_alloc(ctx, (size_t)B * ctx->S * 4, &p->allocs);
+  if (!ok || !p->x_state || !p->mu_buf || !p->eps_buf || !p->d_step || !p->d_zero || !p->fwd_table) {
+    for (void* q : p->allocs) cudaFree(q);
+    delete p;
+    return fail(ctx, IRSDE_ERR_CUDA, err.empty() ? "plan allocation failed" : err);
+  }
+  cudaMemset(p->d_zero, 0, sizeof(int));
+  ctx->plans[key] = p;
+  *out = p;
+  return IRSDE_OK;
+}
+
+void run_forward(irsde_ctx* ctx, Plan* p, cudaStream_t st) {
+  for (auto& op : p->ops) op(p, st);
+}
+
+// default per-timestep scalars in fp32, same op order as the reference's 0-dim tensor math
+void fill_default_coeffs(irsde_ctx* c, int mode, std::vector<float>& tab) {
+  int T = c->T;
+  tab.assign((size_t)(T + 1) * IRSDE_NUM_COEF, 0.f);
+  float dt = c->dt, sqdt = (float)sqrt((double)dt);
+  for (int t = 1; t <= T; ++t) {
+    float* r = &tab[(size_t)t * IRSDE_NUM_COEF];
+    float th = c->thetas[t], sg = c->sigmas[t], cs = c->cumsum[t], cs1 = c->cumsum[t - 1], sb = c->sbars[t];
+    float sg2 = sg * sg;
+    switch (mode) {
+      case IRSDE_MODE_SDE: r[0] = th; r[1] = sg2; r[2] = sb; r[3] = dt; r[4] = sg; r[5] = sqdt; break;
+      case IRSDE_MODE_ODE: r[0] = th; r[1] = 0.5f * sg2; r[2] = sb; r[3] = dt; break;
+      case IRSDE_MODE_POSTERIOR: {
+        float A0 = expf(cs * dt);
+        float A = expf(-th * dt), Bv = expf(-cs * dt), Cv = expf(-cs1 * dt);
+        float term1 = A * (1.f - Cv * Cv) / (1.f - Bv * Bv);
+        float term2 = Cv * (1.f - A * A) / (1.f - Bv * Bv);
+        float A2 = expf(-2.f * th * dt), B2 = expf(-2.f * cs * dt), C2 = expf(-2.f * cs1 * dt);
+        float var = (1.f - A2) * (1.f - C2) / (1.f - B2);
+        float mn = 1e-20f * dt;
+        float lv = logf(var < mn ? mn : var);
+        float sd = expf(0.5f * lv) * c->max_sigma;
+        r[0] = A0; r[1] = sb; r[2] = term1; r[3] = term2; r[4] = sd;
+        break;
+      }
+      case IRSDE_MODE_DSDE_SDE: {
+        float A = expf(-2.f * cs * dt);
+        r[0] = -0.5f * sg2 * (1.f + A); r[1] = sb; r[2] = dt; r[3] = sg; r[4] = sqdt;
+        break;
+      }
+      default: {
+        float A = expf(-2.f * cs * dt);
+        r[0] = -0.5f * sg2 * A; r[1] = sb; r[2] = dt;
+        break;
+      }
+    }
+  }
+}
+
+int upload_coeffs(irsde_ctx* ctx, int mode, const float* tab, int T) {
+  size_t bytes = (size_t)(T + 1) * IRSDE_NUM_COEF * sizeof(float);
+  if (ctx->coef_dev[mode]) {
+    // keep pointer stable across re-uploads of the same T (captured graphs reference it)
+  } else {
+    ctx->coef_dev[mode] = (float*)dev_alloc(ctx, (size_t)(4096 + 1) * IRSDE_NUM_COEF * sizeof(float), &ctx->allocs);
+    if (!ctx->coef_dev[mode]) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc coef failed");
+  }
+  if (T > 4096) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "T > 4096 not supported");
+  CUDA_TRY(ctx, cudaMemcpy(ctx->coef_dev[mode], tab, bytes, cudaMemcpyHostToDevice));
+  return IRSDE_OK;
+}
+
+int ensure_chain_table(irsde_ctx* ctx, Plan* p, int T, cudaStream_t st) {
+  int rows = T + 1;
+  if (rows > p->chain_cap) {
+    int cap = rows < 128 ? 128 : rows;
+    int td = ctx->cfg.nf * 4;
+    p->chain_times = (float*)dev_alloc(ctx, (size_t)cap * 4, &p->allocs);
+    p->chain_temb = (float*)dev_alloc(ctx, (size_t)cap * td * 4, &p->allocs);
+    p->chain_table = (float*)dev_alloc(ctx, (size_t)cap * ctx->S * 4, &p->allocs);
+    if (!p->chain_times || !p->chain_temb || !p->chain_table) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc chain table failed");
+    std::vector<float> tv(cap);
+    for (int i = 0; i < cap; ++i) tv[i] = (float)i;
+    CUDA_TRY(ctx, cudaMemcpy(p->chain_times, tv.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
+    p->chain_cap = cap;
+    for (int m = 0; m < IRSDE_NUM_MODES; ++m)
+      if (p->graph[m]) { cudaGraphExecDestroy(p->graph[m]); p->graph[m] = nullptr; }
+  }
+  launch_time_table(p->chain_times, rows, ctx->cfg.nf, ctx->raw["time_mlp.1.weight"].dev, ctx->raw["time_mlp.1.bias"].dev,
+                    ctx->raw["time_mlp.3.weight"].dev, ctx->raw["time_mlp.3.bias"].dev, ctx->wall, ctx->ball, ctx->S,
+                    p->chain_temb, p->chain_table, st);
+  ctx->launches += 2;
+  return IRSDE_OK;
+}
+
+}  // namespace
+
+// =====================================================================================================
+// C ABI
+// =====================================================================================================
+extern "C" {
+
+const char* irsde_version(void) { return "irsde_b200 0.1 sm_100a"; }
+
+const char* irsde_last_error(const irsde_ctx* ctx) { return ctx ? ctx->err.c_str() : g_last_error.c_str(); }
+
+int irsde_create(const irsde_config* cfg, irsde_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, IRSDE_ERR_INVALID, "null argument");
+  if (cfg->nf < 4 || cfg->nf % 2 || cfg->depth < 1 || cfg->depth > 6 || cfg->in_nc < 1 || cfg->out_nc < 1)
+    return fail(nullptr, IRSDE_ERR_INVALID, "bad network configuration");
+  if (cfg->variant != IRSDE_NET_CONDITIONAL && cfg->variant != IRSDE_NET_DENOISING)
+    return fail(nullptr, IRSDE_ERR_INVALID, "bad variant");
+  if (cfg->precision != IRSDE_PREC_FP32 && cfg->precision != IRSDE_PREC_BF16)
+    return fail(nullptr, IRSDE_ERR_INVALID, "bad precision");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail(nullptr, IRSDE_ERR_CUDA, "no CUDA device available (this library has no CPU path)");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, IRSDE_ERR_INVALID, "bad device ordinal");
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, cfg->device);
+  if (prop.major != 10) return fail(nullptr, IRSDE_ERR_UNSUPPORTED, "irsde_b200 is built for sm_100a (B200) only");
+  irsde_ctx* c = new irsde_ctx();
+  c->cfg = *cfg;
+  if (cudaSetDevice(cfg->device) != cudaSuccess) { delete c; return fail(nullptr, IRSDE_ERR_CUDA, "cudaSetDevice failed"); }
+  std::string terr;
+  c->tc_ok = tc_init(&terr);
+  if (cfg->precision == IRSDE_PREC_BF16 && !c->tc_ok) {
+    delete c;
+    return fail(nullptr, IRSDE_ERR_CUDA, "tensor-core engine init failed: " + terr);
+  }
+  c->use_tc = cfg->precision == IRSDE_PREC_BF16 && !(cfg->reserved & 1);  // reserved bit0: force SIMT (debug)
+  *out = c;
+  return IRSDE_OK;
+}
+
+void irsde_destroy(irsde_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& kv : ctx->plans) {
+    Plan* p = kv.second;
+    for (int m = 0; m < IRSDE_NUM_MODES; ++m)
+      if (p->graph[m]) cudaGraphExecDestroy(p->graph[m]);
+    for (auto* d : p->tc_descs) tc_conv_destroy(d);
+    for (void* q : p->allocs) cudaFree(q);
+    delete p;
+  }
+  for (void* q : ctx->allocs) cudaFree(q);
+  delete ctx;
+}
+
+int irsde_load_tensor(irsde_ctx* ctx, const char* name, const void* data, int32_t ndim, const int64_t* shape) {
+  if (!ctx || !name || !data || ndim < 0 || ndim > 4) return fail(ctx, IRSDE_ERR_INVALID, "bad argument to irsde_load_tensor");
+  cudaSetDevice(ctx->cfg.device);
+  long long n = 1;
+  std::vector<int64_t> sh(shape, shape + ndim);
+  for (auto d : sh) n *= d;
+  RawTensor& t = ctx->raw[name];
+  if (t.dev && t.numel != n) return fail(ctx, IRSDE_ERR_INVALID, std::string("shape change for ") + name);
+  if (!t.dev) {
+    t.dev = (float*)dev_alloc(ctx, (size_t)n * 4, &ctx->allocs);
+    if (!t.dev) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+  }
+  t.shape = sh;
+  t.numel = n;
+  CUDA_TRY(ctx, cudaMemcpy(t.dev, data, (size_t)n * 4, cudaMemcpyDefault));
+  ctx->finalized = false;
+  return IRSDE_OK;
+}
+
+int irsde_finalize_weights(irsde_ctx* ctx) {
+  if (!ctx) return fail(nullptr, IRSDE_ERR_INVALID, "null ctx");
+  cudaSetDevice(ctx->cfg.device);
+  auto specs = param_specs(ctx->cfg);
+  for (auto& s : specs) {
+    auto it = ctx->raw.find(s.name);
+    if (it == ctx->raw.end()) return fail(ctx, IRSDE_ERR_STATE, "missing state-dict entry " + s.name);
+    if (it->second.shape != s.shape) return fail(ctx, IRSDE_ERR_INVALID, "shape mismatch for " + s.name);
+  }
+  if (ctx->raw.size() != specs.size()) return fail(ctx, IRSDE_ERR_INVALID, "unexpected extra state-dict entries");
+  // conv weights -> engine layouts (buffers are allocated once; reload keeps pointers stable)
+  for (auto& s : specs) {
+    if (s.shape.size() != 4) continue;  // vectors / Linear matrices stay fp32 as loaded
+    if (s.name.size() > 2 && s.name.substr(s.name.size() - 2) == ".g") continue;
+    int Cout = (int)s.shape[0], Cin = (int)s.shape[1], KH = (int)s.shape[2], KW = (int)s.shape[3];
+    long long n = (long long)Cout * Cin * KH * KW;
+    float*& ws = ctx->w_simt[s.name];
+    if (!ws) ws = (float*)dev_alloc(ctx, (size_t)n * 4, &ctx->allocs);
+    if (!ws) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+    pack_simt_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, ws, Cout, Cin, KH, KW);
+    if (ctx->cfg.precision == IRSDE_PREC_BF16) {
+      bool is_up = s.name.find(".3.1.weight") != std::string::npos;
+      long long nt = is_up ? (long long)16 * Cout * Cin : n;
+      bf16*& wt = ctx->w_tc[s.name];
+      if (!wt) wt = (bf16*)dev_alloc(ctx, (size_t)nt * 2, &ctx->allocs);
+      if (!wt) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+      if (is_up)
+        pack_tc_up_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cin);
+      else
+        pack_tc_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cin, KH, KW);
+    }
+  }
+  // time-modulation: concatenate every ResBlock's mlp.1 into one [S][4nf] matrix
+  auto rbs = resblocks(ctx->cfg);
+  int td = ctx->cfg.nf * 4, S = 0;
+  for (auto& rb : rbs) { ctx->ss_off[rb.pre] = S; S += 2 * rb.cout; }
+  if (!ctx->wall) {
+    ctx->wall = (float*)dev_alloc(ctx, (size_t)S * td * 4, &ctx->allocs);
+    ctx->ball = (float*)dev_alloc(ctx, (size_t)S * 4, &ctx->allocs);
+    if (!ctx->wall || !ctx->ball) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+  }
+  ctx->S = S;
+  for (auto& rb : rbs) {
+    int off = ctx->ss_off[rb.pre];
+    CUDA_TRY(ctx, cudaMemcpy(ctx->wall + (size_t)off * td, ctx->raw[rb.pre + "mlp.1.weight"].dev, (size_t)2 * rb.cout * td * 4,
+                             cudaMemcpyDeviceToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->ball + off, ctx->raw[rb.pre + "mlp.1.bias"].dev, (size_t)2 * rb.cout * 4, cudaMemcpyDeviceToDevice));
+  }
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  ctx->finalized = true;
+  return IRSDE_OK;
+}
+
+int irsde_set_schedule(irsde_ctx* ctx, const float* thetas, const float* sigmas, const float* thetas_cumsum,
+                       const float* sigma_bars, float dt, float max_sigma, int32_t T) {
+  if (!ctx || !thetas || !sigmas || !thetas_cumsum || !sigma_bars || T < 1) return fail(ctx, IRSDE_ERR_INVALID, "bad schedule");
+  cudaSetDevice(ctx->cfg.device);
+  ctx->T = T; ctx->dt = dt; ctx->max_sigma = max_sigma;
+  ctx->thetas.assign(thetas, thetas + T + 1);
+  ctx->sigmas.assign(sigmas, sigmas + T + 1);
+  ctx->cumsum.assign(thetas_cumsum, thetas_cumsum + T + 1);
+  ctx->sbars.assign(sigma_bars, sigma_bars + T + 1);
+  std::vector<float> tab;
+  for (int m = 0; m < IRSDE_NUM_MODES; ++m) {
+    fill_default_coeffs(ctx, m, tab);
+    int rc = upload_coeffs(ctx, m, tab.data(), T);
+    if (rc) return rc;
+  }
+  ctx->have_sched = true;
+  return IRSDE_OK;
+}
+
+int irsde_set_coeffs(irsde_ctx* ctx, int32_t mode, const float* table, int32_t T) {
+  if (!ctx || !table || mode < 0 || mode >= IRSDE_NUM_MODES) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  if (!ctx->have_sched || T != ctx->T) return fail(ctx, IRSDE_ERR_STATE, "irsde_set_schedule must be called first with the same T");
+  cudaSetDevice(ctx->cfg.device);
+  return upload_coeffs(ctx, mode, table, T);
+}
+
+int irsde_noise_fn(irsde_ctx* ctx, const float* x, const float* mu, const float* times, int32_t n_times, float* out,
+                   int32_t B, int32_t H, int32_t W, void* stream) {
+  if (!ctx || !x || !times || !out) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
+  if (!ctx->finalized) return fail(ctx, IRSDE_ERR_STATE, "weights not finalized");
+  if (ctx->cfg.variant == IRSDE_NET_CONDITIONAL && !mu) return fail(ctx, IRSDE_ERR_INVALID, "mu required for the conditional network");
+  if (n_times != 1 && n_times != B) return fail(ctx, IRSDE_ERR_INVALID, "n_times must be 1 or B");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* p;
+  int rc = build_plan(ctx, B, H, W, &p);
+  if (rc) return rc;
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->fwd_times, times, (size_t)n_times * 4, cudaMemcpyHostToDevice, st));
+  launch_time_table(p->fwd_times, n_times, ctx->cfg.nf, ctx->raw["time_mlp.1.weight"].dev, ctx->raw["time_mlp.1.bias"].dev,
+                    ctx->raw["time_mlp.3.weight"].dev, ctx->raw["time_mlp.3.bias"].dev, ctx->wall, ctx->ball, ctx->S,
+                    p->fwd_temb, p->fwd_table, st);
+  ctx->launches += 2;
+  p->cur.x = x; p->cur.mu = mu; p->cur.out = out;
+  p->cur.ss = p->fwd_table; p->cur.t_ptr = p->d_zero; p->cur.ss_img_stride = (n_times > 1) ? 1 : 0;
+  run_forward(ctx, p, st);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
+int irsde_step(irsde_ctx* ctx, int32_t mode, const float* x, const float* mu, const float* noise, const float* z,
+               int32_t t, float* out, int64_t n, void* stream) {
+  if (!ctx || !x || !noise || !out || mode < 0 || mode >= IRSDE_NUM_MODES) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  if (!ctx->have_sched) return fail(ctx, IRSDE_ERR_STATE, "schedule not set");
+  if (t < 1 || t > ctx->T) return fail(ctx, IRSDE_ERR_INVALID, "t out of range [1,T]");
+  bool need_z = mode == IRSDE_MODE_SDE || mode == IRSDE_MODE_POSTERIOR || mode == IRSDE_MODE_DSDE_SDE;
+  if (need_z && !z) return fail(ctx, IRSDE_ERR_INVALID, "z required for stochastic modes");
+  if (mode <= IRSDE_MODE_POSTERIOR && !mu) return fail(ctx, IRSDE_ERR_INVALID, "mu required for IRSDE modes");
+  cudaSetDevice(ctx->cfg.device);
+  launch_sde_update(mode, x, mu, noise, z, 0, ctx->coef_dev[mode], nullptr, t, out, n, 0, (cudaStream_t)stream);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
+int irsde_reverse(irsde_ctx* ctx, int32_t mode, const float* xT, const float* mu, const float* z, float* x0, int32_t B,
+                  int32_t H, int32_t W, int32_t T, uint64_t seed, int32_t use_graph, void* stream) {
+  if (!ctx || !xT || !x0 || mode < 0 || mode >= IRSDE_NUM_MODES) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  if (!ctx->finalized) return fail(ctx, IRSDE_ERR_STATE, "weights not finalized");
+  if (!ctx->have_sched) return fail(ctx, IRSDE_ERR_STATE, "schedule not set");
+  if (T < 0) T = ctx->T;
+  if (T > ctx->T) return fail(ctx, IRSDE_ERR_INVALID, "T exceeds the schedule length");
+  bool irs = mode <= IRSDE_MODE_POSTERIOR;
+  if (irs != (ctx->cfg.variant == IRSDE_NET_CONDITIONAL))
+    return fail(ctx, IRSDE_ERR_INVALID, "sampler mode does not match the network variant");
+  if (irs && !mu) return fail(ctx, IRSDE_ERR_INVALID, "mu required");
+  if (ctx->cfg.in_nc != ctx->cfg.out_nc) return fail(ctx, IRSDE_ERR_INVALID, "chain needs in_nc == out_nc");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* p;
+  int rc = build_plan(ctx, B, H, W, &p);
+  if (rc) return rc;
+  long long n = (long long)B * ctx->cfg.in_nc * H * W;
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->x_state, xT, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  if (mu) CUDA_TRY(ctx, cudaMemcpyAsync(p->mu_buf, mu, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  if (T == 0) {
+    CUDA_TRY(ctx, cudaMemcpyAsync(x0, p->x_state, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    return IRSDE_OK;
+  }
+  rc = ensure_chain_table(ctx, p, ctx->T, st);
+  if (rc) return rc;
+  launch_set_step(p->d_step, T, 0, z, seed, st);
+  ctx->launches++;
+  p->cur.x = p->x_state; p->cur.mu = p->mu_buf; p->cur.out = p->eps_buf;
+  p->cur.ss = p->chain_table; p->cur.t_ptr = &p->d_step->t; p->cur.ss_img_stride = 0;
+  const float* mu_arg = irs ? p->mu_buf : nullptr;
+  auto one_step = [&](cudaStream_t s) {
+    run_forward(ctx, p, s);
+    launch_sde_update(mode, p->x_state, mu_arg, p->eps_buf, nullptr, n, ctx->coef_dev[mode], p->d_step, 0, p->x_state, n, 0, s);
+    launch_advance_step(p->d_step, s);
+    ctx->launches += 2;
+  };
+  if (use_graph) {
+    if (!p->graph[mode]) {
+      cudaStream_t cs;
+      CUDA_TRY(ctx, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      long long before = ctx->launches;
+      cudaGraph_t g;
+      cudaError_t e = cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        one_step(cs);
+        e = cudaStreamEndCapture(cs, &g);
+      }
+      p->step_launches[mode] = ctx->launches - before;  // kernels in one captured step
+      ctx->launches = before;                            // capture does not execute
+      if (e != cudaSuccess) {
+        cudaStreamDestroy(cs);
+        return fail(ctx, IRSDE_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(e));
+      }
+      e = cudaGraphInstantiate(&p->graph[mode], g, 0);
+      cudaGraphDestroy(g);
+      cudaStreamDestroy(cs);
+      if (e != cudaSuccess) return fail(ctx, IRSDE_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(e));
+    }
+    for (int i = 0; i < T; ++i) CUDA_TRY(ctx, cudaGraphLaunch(p->graph[mode], st));
+    ctx->launches += (long long)T * p->step_launches[mode];
+  } else {
+    for (int i = 0; i < T; ++i) one_step(st);
+  }
+  CUDA_TRY(ctx, cudaMemcpyAsync(x0, p->x_state, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+  CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
+int irsde_noise_state(irsde_ctx* ctx, const float* mu, float* out, int64_t n, uint64_t seed, void* stream) {
+  if (!ctx || !mu || !out) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
+  if (!ctx->have_sched) return fail(ctx, IRSDE_ERR_STATE, "schedule not set");
+  cudaSetDevice(ctx->cfg.device);
+  launch_noise_state(mu, out, n, ctx->max_sigma, seed, (cudaStream_t)stream);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
+int64_t irsde_launch_count(const irsde_ctx* ctx) { return ctx ? ctx->launches : 0; }
+int64_t irsde_device_bytes(const irsde_ctx* ctx) { return ctx ? ctx->dev_bytes : 0; }
+
+int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w, const float* bias, float* y, int32_t B,
+                 int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
+                 int32_t upsample, int32_t silu, void* stream) {
+  if (!ctx || !x || !w || !y) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  int up = upsample ? 2 : 1;
+  if (engine == 1) {
+    // tcgen05 engine: same taps/weight packing as the plan builder
+    std::string terr;
+    if (!tc_init(&terr)) return fail(ctx, IRSDE_ERR_CUDA, "tc_init: " + terr);
+    bool k3 = KH == 3 && KW == 3 && stride == 1 && pad == 1, k1 = KH == 1 && KW == 1 && stride == 1 && pad == 0 && up == 1,
+         k4 = KH == 4 && KW == 4 && stride == 2 && pad == 1 && up == 1 && H % 2 == 0 && W % 2 == 0;
+    if (!(k3 || k1 || k4) || Cin % 8 || Cout % 8) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "shape not supported by the tensor-core engine");
+    int Ho = (H * up + 2 * pad - KH) / stride + 1, Wo = (W * up + 2 * pad - KW) / stride + 1;
+    std::vector<void*> tmp;
+    long long nin = (long long)B * H * W * Cin, nw = (long long)Cout * Cin * KH * KW, nout = (long long)B * Ho * Wo * Cout;
+    long long nwt = (k3 && up == 2) ? (long long)16 * Cout * Cin : nw;
+    bf16* xin = (bf16*)dev_alloc(ctx, nin * 2, &tmp);
+    bf16* xs2d = (bf16*)dev_alloc(ctx, nin * 2, &tmp);
+    bf16* wp = (bf16*)dev_alloc(ctx, nwt * 2, &tmp);
+    bf16* yo = (bf16*)dev_alloc(ctx, nout * 2, &tmp);
+    int rc = IRSDE_OK;
+    TcConvDesc* d = nullptr;
+    if (!xin || !xs2d || !wp || !yo) rc = fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+    if (!rc) {
+      launch_nchw_to_nhwc<bf16>(x, xin, B, Cin, H, W, Cin, st);
+      if (k3 && up == 2) pack_tc_up_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin);
+      else pack_tc_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin, KH, KW);
+      TcTap taps[16];
+      int ntaps = 0, nph = 1, planes = 1, Ha = H, Wa = W;
+      const bf16* a_ptr = xin;
+      if (k3 && up == 1) { for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) taps[ntaps++] = TcTap{r - 1, q - 1, 0}; }
+      else if (k3) { nph = 4; for (int a = 0; a < 2; ++a) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{a - 1, q - 1, 0}; }
+      else if (k1) { taps[ntaps++] = TcTap{0, 0, 0}; }
+      else {
+        static const int PY[4] = {1, 0, 1, 0}, DH[4] = {-1, 0, 0, 1};
+        for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) taps[ntaps++] = TcTap{DH[r], DH[q], PY[r] * 2 + PY[q]};
+        planes = 4; Ha = H / 2; Wa = W / 2;
+        launch_space_to_depth<bf16>(xin, Cin, xs2d, B, H, W, Cin, st);
+        a_ptr = xs2d;
+      }
+      Epilogue ep;
+      memset(&ep, 0, sizeof ep);
+      ep.bias = bias;
+      ep.silu = silu;
+      d = tc_conv_create(a_ptr, Cin, B, Ha, Wa, Cin, planes, wp, Cout, ntaps, taps, nph, ep, yo, Cout, Ho, Wo, &terr);
+      if (!d) rc = fail(ctx, IRSDE_ERR_INVALID, "tc_conv_create: " + terr);
+    }
+    if (!rc) {
+      tc_conv_launch(d, st);
+      launch_nhwc_to_nchw<bf16>(yo, Cout, y, B, Cout, Ho, Wo, st);
+      ctx->launches += 4;
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) e = cudaGetLastError();
+      if (e != cudaSuccess) rc = fail(ctx, IRSDE_ERR_CUDA, std::string("tensor-core conv2d failed: ") + cudaGetErrorString(e));
+    }
+    if (d) tc_conv_destroy(d);
+    for (void* q : tmp) cudaFree(q);
+    return rc;
+  }
+  if (engine != 0) return fail(ctx, IRSDE_ERR_INVALID, "unknown engine");
+  ConvGeom g;
+  g.B = B; g.Hin = H; g.Win = W; g.Cin = Cin; g.up = up; g.KH = KH; g.KW = KW; g.stride = stride; g.pad = pad;
+  g.Hout = (H * up + 2 * pad - KH) / stride + 1;
+  g.Wout = (W * up + 2 * pad - KW) / stride + 1;
+  g.Cout = Cout;
+  std::vector<void*> tmp;
+  long long nin = (long long)B * H * W * Cin, nw = (long long)Cout * Cin * KH * KW, nout = (long long)B * g.Hout * g.Wout * Cout;
+  float* xin = (float*)dev_alloc(ctx, nin * 4, &tmp);
+  float* wp = (float*)dev_alloc(ctx, nw * 4, &tmp);
+  float* yo = (float*)dev_alloc(ctx, nout * 4, &tmp);
+  int rc = IRSDE_OK;
+  if (!xin || !wp || !yo) rc = fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+  if (!rc) {
+    launch_nchw_to_nhwc<float>(x, xin, B, Cin, H, W, Cin, st);
+    pack_simt_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin, KH, KW);
+    Epilogue ep;
+    memset(&ep, 0, sizeof ep);
+    ep.bias = bias;
+    ep.silu = silu;
+    launch_conv_simt<float>(g, xin, Cin, wp, ep, yo, Cout, nullptr, 0, 0, st);
+    launch_nhwc_to_nchw<float>(yo, Cout, y, B, Cout, g.Hout, g.Wout, st);
+    ctx->launches += 4;
+    if (cudaStreamSynchronize(st) != cudaSuccess || cudaGetLastError() != cudaSuccess) rc = fail(ctx, IRSDE_ERR_CUDA, "conv2d failed");
+  }
+  for (void* q : tmp) { cudaFree(q); }
+  return rc;
+}
+
+}  // extern "C"

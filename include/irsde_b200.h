@@ -1,0 +1,126 @@
+/*
+ * irsde_b200 - C ABI of the B200-native IR-SDE / Denoising-SDE reverse-diffusion sampler.
+ *
+ * The reference (Algolzw/image-restoration-sde @ 2598d73) is pure Python and has no FFI; the
+ * calls below are what a binding for its hot path would bind.  Each entry point cites the
+ * reference interface it replaces (paths relative to the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative irsde_status; the message for the last
+ *     failure is available from irsde_last_error(ctx) (ctx may be NULL for create failures);
+ *   - nothing throws across the ABI; one context per device; a context is not thread-safe;
+ *   - image tensors are raw DEVICE pointers to dense fp32 NCHW data ([B,C,H,W], the layout
+ *     the reference's torch tensors have); `stream` is a cudaStream_t passed as void*
+ *     (torch.cuda.current_stream().cuda_stream);
+ *   - weights are copied/repacked by the library; the caller keeps ownership of its buffers.
+ */
+#ifndef IRSDE_B200_H
+#define IRSDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct irsde_ctx irsde_ctx;
+
+typedef enum {
+  IRSDE_OK = 0,
+  IRSDE_ERR_INVALID = -1,     /* bad argument / shape */
+  IRSDE_ERR_CUDA = -2,        /* CUDA runtime / driver error */
+  IRSDE_ERR_STATE = -3,       /* call order (weights / schedule missing) */
+  IRSDE_ERR_UNSUPPORTED = -4  /* configuration this build cannot run */
+} irsde_status;
+
+/* score-network variant */
+#define IRSDE_NET_CONDITIONAL 0 /* codes/config/deraining/models/modules/DenoisingUNet_arch.py:19-134 */
+#define IRSDE_NET_DENOISING 1   /* codes/config/denoising-sde/models/modules/DenoisingUNet_arch.py:19-133 */
+
+/* numerics mode */
+#define IRSDE_PREC_FP32 0 /* parity mode: fp32 storage + fp32 FMA everywhere                     */
+#define IRSDE_PREC_BF16 1 /* perf mode: bf16 activations/weights, tcgen05 MMA, fp32 accumulate,  */
+                          /* fp32 sampler state                                                   */
+
+/* sampler */
+#define IRSDE_MODE_SDE 0       /* IRSDE.reverse_sde        codes/utils/sde_utils.py:252-266 */
+#define IRSDE_MODE_ODE 1       /* IRSDE.reverse_ode        codes/utils/sde_utils.py:268-282 */
+#define IRSDE_MODE_POSTERIOR 2 /* IRSDE.reverse_posterior  codes/utils/sde_utils.py:284-299 */
+#define IRSDE_MODE_DSDE_SDE 3  /* DenoisingSDE.reverse_sde codes/utils/sde_utils.py:483-500 */
+#define IRSDE_MODE_DSDE_ODE 4  /* DenoisingSDE.reverse_ode codes/utils/sde_utils.py:502-522 */
+#define IRSDE_NUM_MODES 5
+#define IRSDE_NUM_COEF 8 /* floats per timestep in a coefficient table */
+
+typedef struct {
+  int32_t in_nc;     /* image channels (ConditionalUNet in_nc)  */
+  int32_t out_nc;    /* output channels                          */
+  int32_t nf;        /* base width                               */
+  int32_t depth;     /* number of levels                         */
+  int32_t variant;   /* IRSDE_NET_*                              */
+  int32_t precision; /* IRSDE_PREC_*                             */
+  int32_t device;    /* CUDA device ordinal                      */
+  int32_t reserved;
+} irsde_config;
+
+/* Replaces `ConditionalUNet(in_nc,out_nc,nf,depth)` + `.to(device)`
+ * (DenoisingUNet_arch.py:20, models/denoising_model.py:36). */
+int irsde_create(const irsde_config* cfg, irsde_ctx** out);
+void irsde_destroy(irsde_ctx* ctx);
+const char* irsde_last_error(const irsde_ctx* ctx);
+/* "irsde_b200 <version> sm_100a" */
+const char* irsde_version(void);
+
+/* Replaces `load_state_dict` (models/base_model.py:92-105): one call per state-dict entry,
+ * `name` and `shape` exactly as in the reference state dict; `data` is fp32, host or device. */
+int irsde_load_tensor(irsde_ctx* ctx, const char* name, const void* data, int32_t ndim, const int64_t* shape);
+/* Check that every tensor of the architecture was loaded and repack for the kernels. */
+int irsde_finalize_weights(irsde_ctx* ctx);
+
+/* Replaces `IRSDE.__init__/_initialize` / `DenoisingSDE._initialize` results
+ * (sde_utils.py:132-149, :419-426): host arrays of length T+1, index 0 unused. */
+int irsde_set_schedule(irsde_ctx* ctx, const float* thetas, const float* sigmas, const float* thetas_cumsum,
+                       const float* sigma_bars, float dt, float max_sigma, int32_t T);
+/* Optional: override the per-timestep scalars of one mode ([T+1][IRSDE_NUM_COEF] host floats)
+ * with values computed by the caller in the reference's own op order. */
+int irsde_set_coeffs(irsde_ctx* ctx, int32_t mode, const float* table, int32_t T);
+
+/* Replaces `IRSDE.noise_fn` -> `ConditionalUNet.forward(xt, cond, time)`
+ * (sde_utils.py:192-194, DenoisingUNet_arch.py:85-134).  `times` is a HOST array of n_times
+ * values (1 = shared by the batch, B = per image); `mu` is ignored for IRSDE_NET_DENOISING. */
+int irsde_noise_fn(irsde_ctx* ctx, const float* x, const float* mu, const float* times, int32_t n_times, float* out,
+                   int32_t B, int32_t H, int32_t W, void* stream);
+
+/* Replaces `reverse_sde_step / reverse_ode_step / reverse_posterior_step`
+ * (sde_utils.py:44-48,219-223,450-462): one fused elementwise update over n floats.
+ * z may be NULL for the ODE modes.  out may alias x. */
+int irsde_step(irsde_ctx* ctx, int32_t mode, const float* x, const float* mu, const float* noise, const float* z,
+               int32_t t, float* out, int64_t n, void* stream);
+
+/* Replaces the whole loop `for t in reversed(range(1, T+1))` of reverse_sde/ode/posterior
+ * (sde_utils.py:252-299, :483-522): network forward + update for t = T..1.
+ * z: [T][B*C*H*W] pre-drawn N(0,1) in loop order (first slice used at t=T), or NULL to draw
+ * in-kernel (Philox4x32-10, seeded with `seed`).  use_graph != 0 replays one captured step graph. */
+int irsde_reverse(irsde_ctx* ctx, int32_t mode, const float* xT, const float* mu, const float* z, float* x0,
+                  int32_t B, int32_t H, int32_t W, int32_t T, uint64_t seed, int32_t use_graph, void* stream);
+
+/* x_T = mu + N(0,1)*max_sigma on the device (sde_utils.py:360-361) with the library's Philox. */
+int irsde_noise_state(irsde_ctx* ctx, const float* mu, float* out, int64_t n, uint64_t seed, void* stream);
+
+/* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
+int64_t irsde_launch_count(const irsde_ctx* ctx);
+/* Bytes of device memory held by the context (weights + workspaces). */
+int64_t irsde_device_bytes(const irsde_ctx* ctx);
+
+/* ---- standalone operator entry points (unit-test / micro-benchmark surface) -------------- */
+/* Generic NHWC convolution through the engine selected by `engine` (0 = fp32 SIMT implicit
+ * GEMM, 1 = tcgen05 bf16 tap-GEMM).  Input/weights/output are fp32 device buffers:
+ * x [B,Cin,H,W], w [Cout,Cin,KH,KW] (nn.Conv2d layout, module_util.py:96,101,105), y
+ * [B,Cout,Ho,Wo]; the call repacks to the engine's layout, runs, and unpacks. */
+int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w, const float* bias, float* y,
+                 int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                 int32_t pad, int32_t upsample, int32_t silu, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IRSDE_B200_H */

@@ -1,0 +1,309 @@
+"""GPU parity tests (B200): the CUDA path, called through the C ABI, against the CPU oracle and the
+golden outputs of the imported reference.  Tolerances are stated per test.
+
+fp32 "parity mode" is held to the north-star bound (1e-3 max-abs per pixel) with large margin;
+bf16 "perf mode" is judged per network forward / teacher-forced step (the chain amplifies
+a 1e-6 perturbation to ~5e-4, so bf16 cannot meet 1e-3 end to end by construction).
+"""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from oracle import irsde_oracle as O
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def _maxdiff(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item()
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import irsde_b200
+    return irsde_b200
+
+
+@pytest.fixture(scope="module")
+def scratch_ctx(lib):
+    _dev()
+    return lib._lib.Context(3, 3, 8, 2, lib._lib.NET_CONDITIONAL, lib._lib.PREC_FP32, 0)
+
+
+def _conv2d(lib, ctx, engine, x, w, bias, stride, pad, up, silu):
+    dev = _dev()
+    xg, wg = x.to(dev).contiguous(), w.to(dev).contiguous()
+    bg = bias.to(dev).contiguous() if bias is not None else None
+    B, Cin, H, W = x.shape
+    Cout, _, KH, KW = w.shape
+    Ho = (H * (2 if up else 1) + 2 * pad - KH) // stride + 1
+    Wo = (W * (2 if up else 1) + 2 * pad - KW) // stride + 1
+    y = torch.empty(B, Cout, Ho, Wo, device=dev)
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    rc = ctx.L.irsde_conv2d(ctx.h, engine, p(xg), p(wg), p(bg), p(y), B, Cin, H, W, Cout, KH, KW, stride, pad,
+                            1 if up else 0, 1 if silu else 0, ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+    lib._lib.check(rc, ctx.h)
+    torch.cuda.synchronize()
+    return y.cpu()
+
+
+def _conv_ref(x, w, bias, stride, pad, up, silu):
+    if up:
+        x = F.interpolate(x, scale_factor=2, mode="nearest")
+    y = F.conv2d(x, w, bias, stride=stride, padding=pad)
+    return F.silu(y) if silu else y
+
+
+CONV_CASES = [
+    # B, Cin, H, W, Cout, K, stride, pad, up, bias, silu
+    (2, 6, 20, 28, 8, 7, 1, 3, False, False, False),    # stem: Cin=6 scalar gather path
+    (2, 16, 12, 20, 24, 3, 1, 1, False, False, True),   # ResBlock conv
+    (1, 32, 9, 7, 16, 1, 1, 0, False, True, False),     # 1x1 with bias, ragged spatial size
+    (2, 8, 16, 24, 16, 4, 2, 1, False, True, False),    # Downsample 4x4 s2 p1
+    (2, 16, 6, 10, 8, 3, 1, 1, True, True, False),      # nearest x2 + 3x3
+    (1, 8, 10, 10, 3, 3, 1, 1, False, True, False),     # head: Cout=3
+    (1, 72, 5, 5, 136, 3, 1, 1, False, False, False),   # several K tiles / two N tiles
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_simt_fp32(lib, scratch_ctx, case):
+    B, Cin, H, W, Cout, K, s, p, up, hb, silu = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5
+    b = torch.randn(Cout, generator=g) if hb else None
+    y = _conv2d(lib, scratch_ctx, 0, x, w, b, s, p, up, silu)
+    assert _maxdiff(y, _conv_ref(x, w, b, s, p, up, silu)) < 2e-5  # fp32, summation order only
+
+
+def test_sde_steps_bitexact(lib, golden):
+    """Fused update kernel vs the reference's own step outputs: same op order, no FMA contraction."""
+    dev = _dev()
+    g = golden["irsde_steps"]
+    sde = lib.IRSDE(*g["args"][:2], schedule=g["args"][2], eps=g["args"][3], device=dev)
+    x, mu, noise = g["x"].to(dev), g["mu"].to(dev), g["noise"].to(dev)
+    for st in g["steps"]:
+        t, z = st["t"], st["z"].to(dev)
+        for mode, key in ((lib._lib.MODE_SDE, "sde"), (lib._lib.MODE_ODE, "ode"), (lib._lib.MODE_POSTERIOR, "posterior")):
+            out = sde._native_step(mode, x, mu, noise, z if key != "ode" else None, t)
+            d = _maxdiff(out, st[key])
+            assert d <= 2e-6, (key, t, d)  # <= 1 ulp of |x|~4 (GPU division/transcendental-free path)
+    g = golden["dsde_steps"]
+    dsde = lib.DenoisingSDE(*g["args"][:2], schedule=g["args"][2], device=dev)
+    x, noise = g["x"].to(dev), g["noise"].to(dev)
+    for st in g["steps"]:
+        z = st["z"].to(dev)
+        assert _maxdiff(dsde._native_step(lib._lib.MODE_DSDE_SDE, x, None, noise, z, st["t"]), st["sde"]) <= 2e-6
+        assert _maxdiff(dsde._native_step(lib._lib.MODE_DSDE_ODE, x, None, noise, None, st["t"]), st["ode"]) <= 2e-6
+
+
+def _net(lib, g, precision="fp32", variant="conditional", force_simt=False):
+    dev = _dev()
+    cls = lib.ConditionalUNet if variant == "conditional" else lib.DenoisingUNet
+    net = cls(3, 3, g["nf"], depth=g["depth"], precision=precision, force_simt=force_simt)
+    net.load_state_dict(g["state"], strict=True)
+    return net.to(dev).eval()
+
+
+def test_unet_forward_fp32(lib, golden):
+    g = golden["unet_cond"]
+    net = _net(lib, g)
+    dev = _dev()
+    y = net(g["xt"].to(dev), g["cond"].to(dev), g["t_int"])
+    assert y.shape == g["y_int"].shape
+    assert _maxdiff(y, g["y_int"]) < 1e-4            # vs the reference's own output (ragged 18x27 -> reflect pad)
+    y2 = net(g["xt"].to(dev), g["cond"].to(dev), g["t_vec"])
+    assert _maxdiff(y2, g["y_vec"]) < 1e-4           # per-image timesteps
+    yo = O.unet_forward(g["state"], g["xt"], g["cond"], g["t_int"], g["nf"], g["depth"])
+    assert _maxdiff(y, yo) < 1e-4                    # vs the oracle
+
+
+def test_unet_forward_fp32_wider(lib):
+    """Larger widths / depth 3 / several K tiles, random weights, CUDA vs oracle."""
+    dev = _dev()
+    P = O.make_weights(3, 3, 16, 3, seed=5)
+    net = lib.ConditionalUNet(3, 3, 16, depth=3, precision="fp32")
+    net.load_state_dict(P, strict=True)
+    net = net.to(dev)
+    g = torch.Generator().manual_seed(9)
+    xt, cond = torch.rand(2, 3, 40, 24, generator=g), torch.rand(2, 3, 40, 24, generator=g)
+    y = net(xt.to(dev), cond.to(dev), 17)
+    yo = O.unet_forward(P, xt, cond, 17, 16, 3)
+    assert _maxdiff(y, yo) < 2e-4
+
+
+def test_unet_denoising_variant_fp32(lib, golden):
+    g = golden["unet_dsde"]
+    net = _net(lib, g, variant="denoising")
+    y = net(g["x"].to(_dev()), g["t_int"])
+    assert _maxdiff(y, g["y"]) < 1e-4
+
+
+@pytest.mark.parametrize("mode", ["sde", "ode", "posterior"])
+@pytest.mark.parametrize("graph", [True, False])
+def test_chain_fp32_vs_reference(lib, golden, mode, graph):
+    """Full T=20 chain (and the partial T=5 chain) against the reference's result, same z.
+    Bound: the north-star 1e-3 max-abs."""
+    dev = _dev()
+    g, u = golden["irsde_chain"], golden["unet_cond"]
+    net = _net(lib, u)
+    sde = lib.IRSDE(g["args"][0], g["args"][1], schedule=g["args"][2], eps=g["args"][3], device=dev)
+    sde.use_graph = graph
+    sde.set_model(net)
+    sde.set_mu(g["lq"].to(dev))
+    c = g["chains"][mode]
+    x0 = getattr(sde, "reverse_" + mode)(g["xT"].to(dev), zs=c["zs"].to(dev))
+    assert _maxdiff(x0, c["x0"]) < 1e-3
+    x5 = getattr(sde, "reverse_" + mode)(g["xT"].to(dev), T=5, zs=c["zs"].to(dev))
+    assert _maxdiff(x5, c["x0_T5"]) < 1e-3
+
+
+def test_chain_stepwise_equals_fused(lib, golden):
+    """Generic python loop (noise_fn + step kernel) == library chain, bit for bit (same kernels)."""
+    dev = _dev()
+    g, u = golden["irsde_chain"], golden["unet_cond"]
+    net = _net(lib, u)
+    sde = lib.IRSDE(g["args"][0], g["args"][1], schedule=g["args"][2], eps=g["args"][3], device=dev)
+    sde.set_model(net)
+    sde.set_mu(g["lq"].to(dev))
+    zs = g["chains"]["sde"]["zs"].to(dev)
+    a = sde.reverse_sde(g["xT"].to(dev), zs=zs)
+    x = g["xT"].to(dev).clone()
+    for i, t in enumerate(reversed(range(1, sde.T + 1))):
+        x = sde._native_step(lib._lib.MODE_SDE, x, sde.mu, sde.noise_fn(x, t), zs[i], t)
+    assert torch.equal(a, x)
+
+
+def test_dsde_chain_fp32(lib, golden):
+    dev = _dev()
+    g = golden["unet_dsde"]
+    net = _net(lib, g, variant="denoising")
+    sde = lib.DenoisingSDE(g["args"][0], g["args"][1], schedule=g["args"][2], device=dev)
+    sde.set_model(net)
+    T = sde.get_optimal_timestep(25)
+    assert int(T) == g["Tstar"]                      # integer work: bit-exact
+    zs = g["zs"].to(dev)
+    assert _maxdiff(sde.reverse_sde(g["x"].to(dev), T=T, zs=zs), g["x0_sde"]) < 1e-3
+    assert _maxdiff(sde.reverse_ode(g["x"].to(dev), T=T), g["x0_ode"]) < 1e-3
+
+
+def test_sharded_equals_unsharded(lib, golden):
+    """Batch slices processed independently == full batch (bit-identical): the multi-GPU partition."""
+    dev = _dev()
+    u = golden["unet_cond"]
+    net = _net(lib, u)
+    sde = lib.IRSDE(10, 10, schedule="cosine", eps=0.005, device=dev)
+    sde.set_model(net)
+    g = torch.Generator().manual_seed(4)
+    lq = torch.rand(3, 3, 16, 16, generator=g).to(dev)
+    xT = lq + torch.randn(3, 3, 16, 16, generator=g).to(dev) * sde.max_sigma
+    zs = torch.randn(10, 3, 3, 16, 16, generator=g).to(dev)
+    sde.set_mu(lq)
+    full = sde.reverse_sde(xT, zs=zs)
+    parts = []
+    for r in range(2):
+        lo, hi = lib.shard_range(3, r, 2)
+        sde.set_mu(lq[lo:hi])
+        parts.append(sde.reverse_sde(xT[lo:hi], zs=zs[:, lo:hi]))
+    assert torch.equal(full, torch.cat(parts))
+
+
+def test_philox_noise_statistics(lib):
+    dev = _dev()
+    sde = lib.IRSDE(10, 4, device=dev)
+    net = lib.ConditionalUNet(3, 3, 8, depth=2).to(dev)
+    sde.set_model(net)
+    ctx = sde._ctx_for(torch.zeros(1, device=dev))
+    mu = torch.zeros(1 << 20, device=dev)
+    out = torch.empty_like(mu)
+    lib._lib.check(ctx.L.irsde_noise_state(ctx.h, ctypes.c_void_p(mu.data_ptr()), ctypes.c_void_p(out.data_ptr()),
+                                           mu.numel(), 123, None), ctx.h)
+    torch.cuda.synchronize()
+    z = out / sde.max_sigma
+    assert abs(z.mean().item()) < 5e-3 and abs(z.std().item() - 1) < 5e-3
+    assert abs((z ** 4).mean().item() - 3) < 0.1
+
+
+# ------------------------------------------------------------------------------------------------
+# bf16 perf mode
+# ------------------------------------------------------------------------------------------------
+TC_CASES = [
+    # B, Cin, H, W, Cout, K, stride, pad, up, bias, silu
+    (1, 64, 16, 16, 64, 1, 1, 0, False, False, False),   # single tap, single K chunk, BN=64
+    (1, 64, 16, 16, 64, 3, 1, 1, False, False, False),   # 9 taps: TMA OOB zero padding
+    (2, 128, 16, 32, 128, 3, 1, 1, False, True, True),   # 2 K chunks, BN=128, bias+SiLU epilogue
+    (1, 192, 8, 8, 256, 3, 1, 1, False, False, False),   # BN=256, 3 K chunks, 8x8 image (BW=8)
+    (2, 72, 10, 12, 40, 3, 1, 1, False, True, False),    # ragged: Cin%64!=0, Cout%32!=0, partial tiles
+    (2, 64, 16, 24, 128, 4, 2, 1, False, True, False),   # downsample over space-to-depth planes
+    (2, 128, 8, 12, 64, 3, 1, 1, True, True, False),     # upsample phases with pre-summed weights
+    (1, 8, 20, 28, 384, 1, 1, 0, False, False, False),   # to_qkv at nf=8: tiny K, 2 N tiles
+]
+
+
+@pytest.mark.parametrize("case", TC_CASES)
+def test_conv_tcgen05(lib, scratch_ctx, case):
+    """tcgen05 tap-GEMM vs fp32 conv on bf16-rounded operands (fp32 accumulation => only the output
+    rounding to bf16 and summation order differ): tolerance 2^-8 relative to the output scale."""
+    B, Cin, H, W, Cout, K, s, p, up, hb, silu = case
+    g = torch.Generator().manual_seed(sum(case[:6]))
+    x = torch.randn(B, Cin, H, W, generator=g).bfloat16().float()
+    w = (torch.randn(Cout, Cin, K, K, generator=g) / (Cin * K * K) ** 0.5)
+    b = torch.randn(Cout, generator=g) if hb else None
+    y = _conv2d(lib, scratch_ctx, 1, x, w, b, s, p, up, silu)
+    if up:
+        # the engine pre-sums weights per output phase before rounding to bf16; compare to the fp32 conv
+        ref = _conv_ref(x, w, b, s, p, up, silu)
+        tol = 3e-2
+    else:
+        ref = _conv_ref(x, w.bfloat16().float(), b, s, p, up, silu)
+        tol = 1.5e-2
+    scale = ref.abs().max().item()
+    assert _maxdiff(y, ref) < tol * max(scale, 1.0), (_maxdiff(y, ref), scale)
+
+
+@pytest.mark.parametrize("force_simt", [True, False])
+def test_unet_forward_bf16(lib, golden, force_simt):
+    """bf16 perf mode (force_simt=True: same bf16 storage through the SIMT engine; False: tcgen05)
+    vs the fp32 oracle on one forward: relative error of a bf16 pipeline (~1e-2 of the output scale)."""
+    dev = _dev()
+    P = O.make_weights(3, 3, 16, 3, seed=5)
+    net = lib.ConditionalUNet(3, 3, 16, depth=3, precision="bf16", force_simt=force_simt)
+    net.load_state_dict(P, strict=True)
+    net = net.to(dev)
+    g = torch.Generator().manual_seed(9)
+    xt, cond = torch.rand(2, 3, 40, 24, generator=g), torch.rand(2, 3, 40, 24, generator=g)
+    y = net(xt.to(dev), cond.to(dev), 17)
+    yo = O.unet_forward(P, xt, cond, 17, 16, 3)
+    scale = yo.abs().max().item()
+    assert _maxdiff(y, yo) < 4e-2 * scale, (_maxdiff(y, yo), scale)
+
+
+def test_step_bf16_teacher_forced(lib, golden):
+    """Per-step bound for perf mode: x_{t-1} from the bf16 network vs the fp32 oracle step, same x_t."""
+    dev = _dev()
+    P = O.make_weights(3, 3, 16, 3, seed=5)
+    net = lib.ConditionalUNet(3, 3, 16, depth=3, precision="bf16")
+    net.load_state_dict(P, strict=True)
+    net = net.to(dev)
+    sde = lib.IRSDE(10, 100, schedule="cosine", eps=0.005, device=dev)
+    sde.set_model(net)
+    sc = O.Schedule(10, 100, "cosine", 0.005)
+    g = torch.Generator().manual_seed(2)
+    lq = torch.rand(1, 3, 32, 32, generator=g)
+    xt = lq + torch.randn(1, 3, 32, 32, generator=g) * sc.max_sigma
+    z = torch.randn(1, 3, 32, 32, generator=g)
+    sde.set_mu(lq.to(dev))
+    for t in (100, 50, 1):
+        eps_o = O.unet_forward(P, xt, lq, t, 16, 3)
+        ref = O.irsde_sde_step(sc, xt, lq, eps_o, z, t)
+        out = sde._native_step(lib._lib.MODE_SDE, xt.to(dev), sde.mu, sde.noise_fn(xt.to(dev), t), z.to(dev), t)
+        assert _maxdiff(out, ref) < 1e-3, (t, _maxdiff(out, ref))

@@ -1,0 +1,129 @@
+"""CPU-side tests: C-ABI exports, host logic (schedules, state-dict contract, sharding plumbing)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    import irsde_b200
+    L = irsde_b200._lib.load()
+    hdr = open(os.path.join(ROOT, "include", "irsde_b200.h")).read()
+    declared = set(re.findall(r"\b(irsde_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(irsde_b200._lib.SYMBOLS)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert b"sm_100a" in L.irsde_version()
+
+
+def test_no_gpu_fails_loudly():
+    import irsde_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(irsde_b200._lib.IrsdeError):
+        irsde_b200._lib.Context(3, 3, 8, 2, 0, 0, 0)
+    net = irsde_b200.ConditionalUNet(3, 3, 8, depth=2)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 3, 8, 8), torch.zeros(1, 3, 8, 8), 1)
+
+
+def test_state_dict_contract(golden):
+    import irsde_b200
+    for key, cls in (("unet_cond", irsde_b200.ConditionalUNet), ("unet_dsde", irsde_b200.DenoisingUNet)):
+        g = golden[key]
+        net = cls(3, 3, g["nf"], depth=g["depth"])
+        assert list(net.state_dict().keys()) == list(g["state"].keys())
+        net.load_state_dict(g["state"], strict=True)
+        wrapped = torch.nn.DataParallel(net) if torch.cuda.is_available() else net
+        assert irsde_b200.sde._unwrap(wrapped) is net
+
+
+def test_schedule_tables_match_reference(golden):
+    import irsde_b200
+    for g in golden["irsde_schedules"]:
+        ms, T, s, eps = g["args"]
+        sde = irsde_b200.IRSDE(ms, T, schedule=s, eps=eps, device="cpu")
+        for k in ("thetas", "sigmas", "thetas_cumsum", "sigma_bars"):
+            assert torch.equal(getattr(sde, k), g[k])
+        assert torch.equal(torch.as_tensor(sde.dt), g["dt"])
+    for g in golden["dsde_schedules"]:
+        ms, T, s = g["args"]
+        sde = irsde_b200.DenoisingSDE(ms, T, schedule=s, device="cpu")
+        assert torch.equal(sde.sigma_bars, g["sigma_bars"])
+        for sg, t in g["optimal_t"].items():
+            assert int(sde.get_optimal_timestep(sg)) == t
+
+
+def test_coeff_tables_reproduce_reference_steps(golden):
+    """The [T+1][8] scalar tables + the kernel's formula (restated in torch) give the reference step."""
+    import irsde_b200
+    L = irsde_b200._lib
+    g = golden["irsde_steps"]
+    sde = irsde_b200.IRSDE(g["args"][0], g["args"][1], schedule=g["args"][2], eps=g["args"][3], device="cpu")
+    x, mu, eps_ = g["x"], g["mu"], g["noise"]
+    for st in g["steps"]:
+        t, z = st["t"], st["z"]
+        c = sde._coeff_table(L.MODE_SDE)[t]
+        out = x - ((c[0] * (mu - x) - c[1] * (-eps_ / c[2])) * c[3]) - c[4] * (z * c[5])
+        assert torch.equal(out, st["sde"])
+        c = sde._coeff_table(L.MODE_POSTERIOR)[t]
+        x0 = (x - mu - c[1] * eps_) * c[0] + mu
+        out = c[2] * (x - mu) + c[3] * (x0 - mu) + mu + c[4] * z
+        assert torch.equal(out, st["posterior"])
+
+
+def test_shard_range_partition():
+    import irsde_b200
+    for B in (1, 3, 8, 32, 33):
+        for R in (1, 2, 4, 8):
+            cover = []
+            for r in range(R):
+                lo, hi = irsde_b200.shard_range(B, r, R)
+                cover += list(range(lo, hi))
+            assert cover == list(range(B))
+
+
+def _worker(rank, world, port, q):
+    import torch.distributed as dist
+    import irsde_b200
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    xT = torch.arange(5 * 3 * 2 * 2, dtype=torch.float32).reshape(5, 3, 2, 2)
+    mu = xT * 0.5
+    zs = torch.arange(4 * 5 * 3 * 2 * 2, dtype=torch.float32).reshape(4, 5, 3, 2, 2)
+    run = lambda x, m, z: x * 2 + m + z.sum(0)  # stand-in for the per-rank chain (needs no GPU)
+    out = irsde_b200.sharded_reverse(run, xT, mu, zs)
+    lin = torch.nn.Linear(4, 4)
+    if rank != 0:
+        with torch.no_grad():
+            for p in lin.parameters():
+                p.zero_()
+    irsde_b200.broadcast_weights(lin, src=0)
+    q.put((rank, out, torch.cat([p.detach().reshape(-1) for p in lin.parameters()])))
+    dist.destroy_process_group()
+
+
+def test_sharded_gather_gloo_world2():
+    """world_size=2 gloo: partition, per-rank run, all_gather order, one-shot weight broadcast."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(60)
+    xT = torch.arange(5 * 3 * 2 * 2, dtype=torch.float32).reshape(5, 3, 2, 2)
+    zs = torch.arange(4 * 5 * 3 * 2 * 2, dtype=torch.float32).reshape(4, 5, 3, 2, 2)
+    expect = xT * 2 + xT * 0.5 + zs.sum(0)
+    for rank, out, w in res:
+        assert torch.equal(out, expect)
+    assert torch.equal(res[0][2], res[1][2]) and res[0][2].abs().sum() > 0
