@@ -17,7 +17,8 @@ NUM_COEF = 8
 # every symbol include/irsde_b200.h declares
 SYMBOLS = ["irsde_create", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
            "irsde_finalize_weights", "irsde_set_schedule", "irsde_set_coeffs", "irsde_noise_fn", "irsde_step",
-           "irsde_reverse", "irsde_noise_state", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d"]
+           "irsde_reverse", "irsde_noise_state", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
+           "irsde_profile_end"]
 
 
 class Config(ctypes.Structure):
@@ -69,6 +70,11 @@ def load():
     L.irsde_device_bytes.restype = i64
     L.irsde_conv2d.argtypes = [vp, i32, vp, vp, vp, vp] + [i32] * 11 + [vp]
     L.irsde_conv2d.restype = ctypes.c_int
+    L.irsde_profile_begin.argtypes = [vp]
+    L.irsde_profile_begin.restype = ctypes.c_int
+    L.irsde_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                    ctypes.POINTER(i64), i32]
+    L.irsde_profile_end.restype = ctypes.c_int
     _lib = L
     return L
 

@@ -1,0 +1,450 @@
+// HBM-bound kernels around the attention sites of the UNet: channel LayerNorm, LinearAttention
+// (module_util.py:150-178) and the full softmax Attention of the denoising-sde variant (:182-204).
+// All loads/stores are 128-bit vectors over the NHWC channel dimension; math is fp32.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace irsde {
+
+// accurate exp in parity (fp32) mode, fast exp in perf (bf16) mode
+template <typename T>
+__device__ __forceinline__ float fexp(float x);
+template <>
+__device__ __forceinline__ float fexp<float>(float x) { return expf(x); }
+template <>
+__device__ __forceinline__ float fexp<bf16>(float x) { return __expf(x); }
+
+// ---- 16-byte vector access over float / bf16 ----------------------------------------------------
+template <typename T>
+struct VecIO;
+template <>
+struct VecIO<float> {
+  static constexpr int N = 4;
+  static __device__ __forceinline__ void load(const float* p, float* v) {
+    float4 t = *reinterpret_cast<const float4*>(p);
+    v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
+  }
+  static __device__ __forceinline__ void store(float* p, const float* v) {
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+};
+template <>
+struct VecIO<bf16> {
+  static constexpr int N = 8;
+  static __device__ __forceinline__ void load(const bf16* p, float* v) {
+    uint4 t = *reinterpret_cast<const uint4*>(p);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+  }
+  static __device__ __forceinline__ void store(bf16* p, const float* v) {
+    uint4 t;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    *reinterpret_cast<uint4*>(p) = t;
+  }
+};
+
+// =============================================================================================
+// channel LayerNorm: (x-mean)*rsqrt(var_biased+1e-5)*g (+ residual)   module_util.py:70-79,20-26
+// `lpp` lanes cooperate on one pixel (lpp = 32 for wide C, fewer for narrow C so a warp covers
+// several pixels with full 16-byte loads); the row is held in registers between the two passes.
+// =============================================================================================
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict__ x, int x_pitch,
+                                                            const float* __restrict__ g, const T* __restrict__ res,
+                                                            int res_pitch, T* __restrict__ out, int out_pitch,
+                                                            long long npix, int C, int lpp) {
+  constexpr int N = VecIO<T>::N;
+  const int lane = threadIdx.x & 31;
+  const int ppw = 32 / lpp;
+  const long long warp_g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const long long pix = warp_g * ppw + lane / lpp;
+  const int sub = lane % lpp;
+  const int nvec = C / N;
+  const bool valid = pix < npix;
+  float v[MAXV][N];
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = sub + k * lpp;
+    if (valid && i < nvec) {
+      VecIO<T>::load(x + pix * x_pitch + i * N, v[k]);
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += v[k][j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[k][j] = 0.f;
+    }
+  }
+  for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = sub + k * lpp;
+    if (i < nvec) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) { float d = v[k][j] - mean; q += d * d; }
+    }
+  }
+  for (int o = lpp >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)C + 1e-5f);
+  if (!valid) return;
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k) {
+    const int i = sub + k * lpp;
+    if (i < nvec) {
+      float y[N], r[N];
+#pragma unroll
+      for (int j = 0; j < N; j += 4) {
+        float4 gg = *reinterpret_cast<const float4*>(g + i * N + j);
+        y[j] = (v[k][j] - mean) * rstd * gg.x;
+        y[j + 1] = (v[k][j + 1] - mean) * rstd * gg.y;
+        y[j + 2] = (v[k][j + 2] - mean) * rstd * gg.z;
+        y[j + 3] = (v[k][j + 3] - mean) * rstd * gg.w;
+      }
+      if (res) {
+        VecIO<T>::load(res + pix * res_pitch + i * N, r);
+#pragma unroll
+        for (int j = 0; j < N; ++j) y[j] += r[j];
+      }
+      VecIO<T>::store(out + pix * out_pitch + i * N, y);
+    }
+  }
+}
+
+// scalar fallback (any C / alignment): one warp per pixel, three cached passes
+template <typename T>
+__global__ void layernorm_scalar_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
+                                        const T* __restrict__ res, int res_pitch, T* __restrict__ out, int out_pitch,
+                                        long long npix, int C) {
+  int lane = threadIdx.x & 31;
+  long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= npix) return;
+  const T* xr = x + pix * x_pitch;
+  float s = 0.f;
+  for (int c = lane; c < C; c += 32) s += to_f(xr[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / (float)C;
+  float v = 0.f;
+  for (int c = lane; c < C; c += 32) { float d = to_f(xr[c]) - mean; v += d * d; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  float rstd = 1.0f / sqrtf(v / (float)C + 1e-5f);
+  T* orow = out + pix * out_pitch;
+  const T* rr = res ? res + pix * res_pitch : nullptr;
+  for (int c = lane; c < C; c += 32) {
+    float y = (to_f(xr[c]) - mean) * rstd * g[c];
+    if (rr) y += to_f(rr[c]);
+    orow[c] = from_f<T>(y);
+  }
+}
+
+template <typename T>
+void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int res_pitch, T* out, int out_pitch,
+                      long long npix, int C, cudaStream_t st) {
+  constexpr int N = VecIO<T>::N;
+  bool vec_ok = C % N == 0 && x_pitch % N == 0 && out_pitch % N == 0 && ((uintptr_t)x % 16 == 0) &&
+                ((uintptr_t)out % 16 == 0) && ((uintptr_t)g % 16 == 0) &&
+                (!res || (res_pitch % N == 0 && (uintptr_t)res % 16 == 0));
+  int nvec = C / N;
+  int lpp = 1;
+  while (lpp * 2 <= 32 && lpp * 2 <= nvec) lpp *= 2;
+  int per_lane = vec_ok ? (nvec + lpp - 1) / lpp : 999;
+  if (!vec_ok || per_lane > 16) {
+    const int warps = 8;
+    layernorm_scalar_kernel<T><<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch,
+                                                                                            out, out_pitch, npix, C);
+    return;
+  }
+  const int warps = 8;
+  long long pix_per_block = (long long)warps * (32 / lpp);
+  unsigned grid = (unsigned)((npix + pix_per_block - 1) / pix_per_block);
+#define LN_LAUNCH(MV) \
+  layernorm_vec_kernel<T, MV><<<grid, warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch, out, out_pitch, npix, C, lpp)
+  if (per_lane <= 1) LN_LAUNCH(1);
+  else if (per_lane <= 2) LN_LAUNCH(2);
+  else if (per_lane <= 4) LN_LAUNCH(4);
+  else if (per_lane <= 8) LN_LAUNCH(8);
+  else LN_LAUNCH(16);
+#undef LN_LAUNCH
+}
+template void launch_layernorm<float>(const float*, int, const float*, const float*, int, float*, int, long long, int,
+                                      cudaStream_t);
+template void launch_layernorm<bf16>(const bf16*, int, const float*, const bf16*, int, bf16*, int, long long, int,
+                                     cudaStream_t);
+
+// =============================================================================================
+// LinearAttention core (module_util.py:163-177).  heads=4, dim_head=32 (fixed by the reference).
+// qkv channel layout: [q(4x32) | k(4x32) | v(4x32)], head h = channels h*32..h*32+31 of each third.
+//   pass A (la_kv): each block streams chunks of 64 pixels of ONE image, all 4 heads, keeping running
+//           (max, sum, ctx[32x32]) per head with the online-softmax rescale; one partial per block
+//   pass B (la_combine): merge the per-block partials: ctx[d][e] = sum_n softmax_n(k)[d,n] v[e,n] / N
+//   pass C (la_out): per pixel/head: q = softmax_d(q) * 32^-.5 ; out[e] = sum_d ctx[d][e] q[d]
+// =============================================================================================
+static const int LA_PIX = 64;               // pixels per chunk
+static const int LA_REC = 4 * (64 + 1024);  // floats per partial record (4 heads x (m[32], s[32], ctx[32][32]))
+static const int LA_MAXBLK = 64;            // partial records per image
+
+static int la_blocks_per_image(int B, int N) {
+  int nchunks = (N + LA_PIX - 1) / LA_PIX;
+  int nblk = (444 + B - 1) / B;
+  if (nblk > LA_MAXBLK) nblk = LA_MAXBLK;
+  if (nblk > nchunks) nblk = nchunks;
+  return nblk < 1 ? 1 : nblk;
+}
+size_t linattn_partial_floats(int B, int N) { return (size_t)B * LA_MAXBLK * LA_REC; }
+
+template <typename T>
+__global__ void __launch_bounds__(256) la_kv_kernel(const T* __restrict__ qkv, int pitch, float* __restrict__ part,
+                                                    int N, int nchunks, int nblk) {
+  extern __shared__ __align__(16) float la_sm[];
+  float (*ks)[128] = reinterpret_cast<float (*)[128]>(la_sm);               // [64][128] k -> p
+  float (*vs)[128] = reinterpret_cast<float (*)[128]>(la_sm + LA_PIX * 128);  // [64][128]
+  float* m_run = la_sm + 2 * LA_PIX * 128;  // [128]
+  float* s_run = m_run + 128;               // [128]
+  float* alpha_s = s_run + 128;             // [128]
+  float* red = alpha_s + 128;               // [2][128] scratch
+  constexpr int NV = VecIO<T>::N;
+  const int tid = threadIdx.x, b = blockIdx.y, blk = blockIdx.x;
+  if (tid < 128) { m_run[tid] = -INFINITY; s_run[tid] = 0.f; }
+  const int h = tid >> 6, d = (tid & 63) >> 1, e0 = (tid & 1) * 16;
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  const int c = tid & 127, half = tid >> 7;
+  const int c0 = (int)(((long long)nchunks * blk) / nblk), c1 = (int)(((long long)nchunks * (blk + 1)) / nblk);
+  for (int ch = c0; ch < c1; ++ch) {
+    const int n0 = ch * LA_PIX;
+    __syncthreads();  // previous chunk fully consumed
+    // ---- load k,v (256 contiguous channels per pixel) with 16-byte vectors
+    constexpr int VPP = 256 / NV;  // vectors per pixel
+    for (int i = tid; i < LA_PIX * VPP; i += 256) {
+      const int n = i / VPP, j = i - n * VPP;
+      float tmp[NV];
+      const bool ok = n0 + n < N;
+      if (ok) VecIO<T>::load(qkv + ((long long)b * N + n0 + n) * pitch + 128 + j * NV, tmp);
+      const int cc = j * NV;  // 0..255 : [0,128) = k, [128,256) = v
+#pragma unroll
+      for (int q = 0; q < NV; ++q) {
+        if (cc < 128) ks[n][cc + q] = ok ? tmp[q] : -INFINITY;
+        else vs[n][cc - 128 + q] = ok ? tmp[q] : 0.f;
+      }
+    }
+    __syncthreads();
+    // ---- per-channel running max / exp / sum (online softmax over the pixel axis)
+    float mx = -INFINITY;
+#pragma unroll 8
+    for (int n = half * 32; n < half * 32 + 32; ++n) mx = fmaxf(mx, ks[n][c]);
+    red[half * 128 + c] = mx;
+    __syncthreads();
+    const float m_old = m_run[c];
+    const float m_new = fmaxf(m_old, fmaxf(red[c], red[128 + c]));
+    float ps = 0.f;
+#pragma unroll 8
+    for (int n = half * 32; n < half * 32 + 32; ++n) {
+      float p = fexp<T>(ks[n][c] - m_new);
+      ks[n][c] = p;
+      ps += p;
+    }
+    __syncthreads();  // everyone has read red[] / m_run
+    red[half * 128 + c] = ps;
+    __syncthreads();
+    if (half == 0) {
+      const float al = fexp<T>(m_old - m_new);  // exp(-inf) = 0 on the first chunk
+      alpha_s[c] = al;
+      s_run[c] = s_run[c] * al + red[c] + red[128 + c];
+      m_run[c] = m_new;
+    }
+    __syncthreads();
+    // ---- ctx[h][d][e0..e0+15] += sum_n p[n][h*32+d] * v[n][h*32+e]
+    const float al = alpha_s[h * 32 + d];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) acc[j] *= al;
+#pragma unroll 4
+    for (int n = 0; n < LA_PIX; ++n) {
+      const float p = ks[n][h * 32 + d];
+      const float4* vp = reinterpret_cast<const float4*>(&vs[n][h * 32 + e0]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 vv = vp[j];
+        acc[4 * j] += p * vv.x;
+        acc[4 * j + 1] += p * vv.y;
+        acc[4 * j + 2] += p * vv.z;
+        acc[4 * j + 3] += p * vv.w;
+      }
+    }
+  }
+  __syncthreads();
+  float* rec = part + ((long long)b * LA_MAXBLK + blk) * LA_REC;
+  if (tid < 128) {
+    const int hh = tid >> 5, dd = tid & 31;
+    rec[hh * 1088 + dd] = m_run[tid];
+    rec[hh * 1088 + 32 + dd] = s_run[tid];
+  }
+  float* cp = rec + h * 1088 + 64 + d * 32 + e0;
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(cp + j) = make_float4(acc[j], acc[j + 1], acc[j + 2], acc[j + 3]);
+}
+
+__global__ void __launch_bounds__(1024) la_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx,
+                                                          int N, int nblk) {
+  const int bh = blockIdx.x, b = bh >> 2, h = bh & 3, tid = threadIdx.x;
+  const int d = tid >> 5;
+  const float* base = part + (long long)b * LA_MAXBLK * LA_REC + h * 1088;
+  float M = -INFINITY;
+  for (int k = 0; k < nblk; ++k) M = fmaxf(M, base[(long long)k * LA_REC + d]);
+  float S = 0.f, acc = 0.f;
+  for (int k = 0; k < nblk; ++k) {
+    const float* rec = base + (long long)k * LA_REC;
+    const float w = expf(rec[d] - M);
+    S += rec[32 + d] * w;
+    acc += rec[64 + tid] * w;
+  }
+  ctx[(long long)bh * 1024 + tid] = acc / S / (float)N;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) la_out_kernel(const T* __restrict__ qkv, int pitch, const float* __restrict__ ctx,
+                                                     T* __restrict__ hidden, int hid_pitch, int N) {
+  __shared__ __align__(16) float cs[4][32][32];
+  constexpr int NV = VecIO<T>::N;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  for (int i = tid; i < 1024; i += 256)
+    reinterpret_cast<float4*>(&cs[0][0][0])[i] = reinterpret_cast<const float4*>(ctx + (long long)b * 4096)[i];
+  __syncthreads();
+  const int h = tid >> 6;
+  const int n = blockIdx.x * 64 + (tid & 63);
+  if (n >= N) return;
+  const T* row = qkv + ((long long)b * N + n) * pitch + h * 32;
+  float q[32];
+#pragma unroll
+  for (int j = 0; j < 32; j += NV) VecIO<T>::load(row + j, q + j);
+  float m = q[0];
+#pragma unroll
+  for (int dd = 1; dd < 32; ++dd) m = fmaxf(m, q[dd]);
+  float s = 0.f;
+#pragma unroll
+  for (int dd = 0; dd < 32; ++dd) { q[dd] = fexp<T>(q[dd] - m); s += q[dd]; }
+  const float sc = 0.17677669529663687f / s;  // softmax normaliser * 32^-0.5
+  float o[32];
+#pragma unroll
+  for (int e = 0; e < 32; ++e) o[e] = 0.f;
+#pragma unroll
+  for (int dd = 0; dd < 32; ++dd) {
+    const float qd = q[dd] * sc;
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+      float4 cc = *reinterpret_cast<const float4*>(&cs[h][dd][e]);
+      o[e] += cc.x * qd;
+      o[e + 1] += cc.y * qd;
+      o[e + 2] += cc.z * qd;
+      o[e + 3] += cc.w * qd;
+    }
+  }
+  T* orow = hidden + ((long long)b * N + n) * hid_pitch + h * 32;
+#pragma unroll
+  for (int j = 0; j < 32; j += NV) VecIO<T>::store(orow + j, o + j);
+}
+
+static bool g_la_attr_done = false;
+
+template <typename T>
+void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
+                    cudaStream_t st) {
+  const int nchunks = (N + LA_PIX - 1) / LA_PIX;
+  const int nblk = la_blocks_per_image(B, N);
+  const size_t smem = (size_t)(2 * LA_PIX * 128 + 128 * 5) * sizeof(float);
+  if (!g_la_attr_done) {
+    cudaFuncSetAttribute(la_kv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(la_kv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    g_la_attr_done = true;
+  }
+  la_kv_kernel<T><<<dim3(nblk, B), 256, smem, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+  la_combine_kernel<<<B * 4, 1024, 0, st>>>(partial, ctx, N, nblk);
+  la_out_kernel<T><<<dim3((N + 63) / 64, B), 256, 0, st>>>(qkv, qkv_pitch, ctx, hidden, hid_pitch, N);
+}
+template void launch_linattn<float>(const float*, int, float*, float*, float*, int, int, int, cudaStream_t);
+template void launch_linattn<bf16>(const bf16*, int, float*, float*, bf16*, int, int, int, cudaStream_t);
+
+// =============================================================================================
+// full softmax attention (module_util.py:192-204) - denoising-sde mid_attn only.
+// thread per query, keys/values staged through shared memory, online softmax.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(128) fullattn_kernel(const T* __restrict__ qkv, int pitch, T* __restrict__ hidden,
+                                                       int hid_pitch, int N) {
+  __shared__ __align__(16) float ks[64][32];
+  __shared__ __align__(16) float vs[64][32];
+  int bh = blockIdx.y, b = bh >> 2, h = bh & 3;
+  int tid = threadIdx.x;
+  int i = blockIdx.x * 128 + tid;
+  bool valid = i < N;
+  float q[32], acc[32];
+  const float scale = 0.17677669529663687f;
+  if (valid) {
+    const T* row = qkv + ((long long)b * N + i) * pitch + h * 32;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) q[d] = to_f(row[d]) * scale;
+  } else {
+#pragma unroll
+    for (int d = 0; d < 32; ++d) q[d] = 0.f;
+  }
+#pragma unroll
+  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
+  float m = -INFINITY, l = 0.f;
+  for (int j0 = 0; j0 < N; j0 += 64) {
+    __syncthreads();
+    for (int t = tid; t < 64 * 32; t += 128) {
+      int j = t >> 5, d = t & 31;
+      float kv = 0.f, vv = 0.f;
+      if (j0 + j < N) {
+        const T* row = qkv + ((long long)b * N + j0 + j) * pitch;
+        kv = to_f(row[128 + h * 32 + d]);
+        vv = to_f(row[256 + h * 32 + d]);
+      }
+      ks[j][d] = kv;
+      vs[j][d] = vv;
+    }
+    __syncthreads();
+    int jmax = min(64, N - j0);
+    for (int j = 0; j < jmax; ++j) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 32; d += 4) {
+        float4 k4 = *reinterpret_cast<const float4*>(&ks[j][d]);
+        s += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
+      }
+      float mn = fmaxf(m, s);
+      float alpha = expf(m - mn);
+      float p = expf(s - mn);
+      l = l * alpha + p;
+#pragma unroll
+      for (int d = 0; d < 32; d += 4) {
+        float4 v4 = *reinterpret_cast<const float4*>(&vs[j][d]);
+        acc[d] = acc[d] * alpha + p * v4.x;
+        acc[d + 1] = acc[d + 1] * alpha + p * v4.y;
+        acc[d + 2] = acc[d + 2] * alpha + p * v4.z;
+        acc[d + 3] = acc[d + 3] * alpha + p * v4.w;
+      }
+      m = mn;
+    }
+  }
+  if (valid) {
+    T* orow = hidden + ((long long)b * N + i) * hid_pitch + h * 32;
+#pragma unroll
+    for (int d = 0; d < 32; ++d) orow[d] = from_f<T>(acc[d] / l);
+  }
+}
+template <typename T>
+void launch_fullattn(const T* qkv, int qkv_pitch, T* hidden, int hid_pitch, int B, int N, cudaStream_t st) {
+  fullattn_kernel<T><<<dim3((N + 127) / 128, B * 4), 128, 0, st>>>(qkv, qkv_pitch, hidden, hid_pitch, N);
+}
+template void launch_fullattn<float>(const float*, int, float*, int, int, int, cudaStream_t);
+template void launch_fullattn<bf16>(const bf16*, int, bf16*, int, int, int, cudaStream_t);
+
+}  // namespace irsde

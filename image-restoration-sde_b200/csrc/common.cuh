@@ -63,7 +63,8 @@ void launch_conv_simt(const ConvGeom& g, const T* in, int in_pitch, const float*
 // ---- elementwise / reduction kernels (elementwise.cu) -----------------------------------------
 template <typename T>
 void launch_prep_input(const float* xt, const float* cond, T* out, int B, int C, int H, int W, int Hp, int Wp,
-                       int out_pitch, int conditional, cudaStream_t st);
+                       int out_pitch, int conditional, cudaStream_t st, int pad_top = 0, int pad_left = 0, int row_pix = 0,
+                       int img_rows = 0);
 template <typename T>
 void launch_nchw_to_nhwc(const float* in, T* out, int B, int C, int H, int W, int out_pitch, cudaStream_t st);
 template <typename T>
@@ -113,6 +114,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
                            int Hout, int Wout, std::string* err);
 void tc_conv_destroy(TcConvDesc*);
 void tc_conv_set_runtime(TcConvDesc*, const float* ss, const int* t_ptr, int ss_img_stride);
+void tc_conv_set_out_nchw(TcConvDesc*, float* out, int cropH, int cropW);  // out==nullptr at create => fp32 NCHW output
 int tc_conv_launch(TcConvDesc*, cudaStream_t st);  // returns number of launches (1), <0 on error
 bool tc_init(std::string* err);                    // resolves cuTensorMapEncodeTiled
 

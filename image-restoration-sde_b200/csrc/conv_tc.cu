@@ -40,6 +40,8 @@ struct TcParams {
   int Hout, Wout, os;   // output spatial size and output stride (2 for the upsample phases)
   bf16* out;
   int out_pitch;
+  float* out_nchw;      // if set: write fp32 NCHW cropped to (cropH, cropW) instead of the NHWC view
+  int cropH, cropW;
   const bf16* res;
   int res_pitch;
   const float* bias;
@@ -275,7 +277,20 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (pvalid) {
+      if (pvalid && P.out_nchw) {
+        if (hh < P.cropH && ww < P.cropW) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = n0 + c0 + j;
+            if (n < P.Cout) {
+              float x = __uint_as_float(v[j]);
+              x = (x + s_epi[2 * BN + c0 + j]) * s_epi[c0 + j] + s_epi[BN + c0 + j];
+              if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
+              P.out_nchw[(((long long)b * P.Cout + n) * P.cropH + hh) * P.cropW + ww] = x;
+            }
+          }
+        }
+      } else if (pvalid) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {  // groups of 8 channels = one 16-byte store
           const int cg = c0 + g * 8;
@@ -355,7 +370,10 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   };
   if (!g_encode) return bad("tc_init not called");
   if (ntaps < 1 || ntaps > 16) return bad("ntaps out of range");
-  if (Cin % 8 || Cout % 8 || in_pitch % 8 || out_pitch % 8) return bad("channel counts / pitches must be multiples of 8");
+  const bool nchw_out = (out == nullptr);  // caller sets the fp32 NCHW pointer at launch (tc_conv_set_out_nchw)
+  const int Cout_w = (Cout + 7) / 8 * 8;   // rows of the packed weight tensor (zero padded)
+  if (Cin % 8 || in_pitch % 8) return bad("input channel count / pitch must be multiples of 8");
+  if (!nchw_out && (Cout % 8 || out_pitch % 8)) return bad("output channel count / pitch must be multiples of 8");
   if (((uintptr_t)in & 15) || ((uintptr_t)wpacked & 15) || ((uintptr_t)out & 15)) return bad("operands must be 16-byte aligned");
   if (ep.res && (((uintptr_t)ep.res & 15) || ep.res_pitch % 8)) return bad("residual must be 16-byte aligned");
   TcConvDesc* d = new TcConvDesc();
@@ -389,6 +407,14 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B, (cuuint64_t)planes};
     cuuint64_t strides[4] = {(cuuint64_t)in_pitch * 2, (cuuint64_t)Win * in_pitch * 2, (cuuint64_t)Hin * Win * in_pitch * 2,
                              (cuuint64_t)B * Hin * Win * in_pitch * 2};
+    if (planes < 0) {
+      // 7x7 stem "row trick": the input is a zero-bordered [B][H+6][W+8][8ch] buffer; one GEMM K-chunk of
+      // 64 elements = 8 consecutive pixels x 8 channels of one input row (overlapping pixel stride of 16 B),
+      // so kernel row r is a single tap (dh=r) and K = 7 x 64.
+      dims[0] = 64; dims[1] = (cuuint64_t)Win; dims[2] = (cuuint64_t)(Hin + 6); dims[3] = (cuuint64_t)B; dims[4] = 1;
+      strides[0] = 16; strides[1] = (cuuint64_t)(Win + 8) * 16; strides[2] = (cuuint64_t)(Hin + 6) * (Win + 8) * 16;
+      strides[3] = strides[2] * B;
+    }
     cuuint32_t box[5] = {64, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1, 1};
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(&d->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in, dims, strides, box, es,
@@ -402,8 +428,8 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   }
   // B: [phase*ntaps][Cout][Cin]
   {
-    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout, (cuuint64_t)(nphases * ntaps)};
-    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout * Cin * 2};
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout_w, (cuuint64_t)(nphases * ntaps)};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout_w * Cin * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = g_encode(&d->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)wpacked, dims, strides, box, es,
@@ -419,6 +445,12 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
 }
 
 void tc_conv_destroy(TcConvDesc* d) { delete d; }
+
+void tc_conv_set_out_nchw(TcConvDesc* d, float* out, int cropH, int cropW) {
+  d->P.out_nchw = out;
+  d->P.cropH = cropH;
+  d->P.cropW = cropW;
+}
 
 void tc_conv_set_runtime(TcConvDesc* d, const float* ss, const int* t_ptr, int ss_img_stride) {
   d->P.ss = ss;

@@ -1,5 +1,5 @@
-// Memory-bound kernels of the IR-SDE hot path: input packing, channel LayerNorm, linear / full
-// attention, timestep-embedding table, and the fused sampler update.  All fp32 math; activations
+// Memory-bound kernels of the IR-SDE hot path: input packing, timestep-embedding table, the fused
+// sampler update and layout helpers (LayerNorm / attention live in attention.cu).  All fp32 math; activations
 // are float (parity mode) or bf16 (perf mode).
 #include <math.h>
 
@@ -13,7 +13,8 @@ namespace irsde {
 // =============================================================================================
 template <typename T>
 __global__ void prep_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond, T* __restrict__ out,
-                                  int B, int C, int H, int W, int Hp, int Wp, int pitch, int conditional) {
+                                  int B, int C, int H, int W, int Hp, int Wp, int pitch, int conditional,
+                                  int pad_top, int pad_left, int row_pix, int img_rows) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Hp * Wp;
   if (idx >= total) return;
@@ -22,7 +23,8 @@ __global__ void prep_input_kernel(const float* __restrict__ xt, const float* __r
   int b = idx / ((long long)Wp * Hp);
   int h = hp < H ? hp : 2 * (H - 1) - hp;  // reflect (no edge repeat)
   int w = wp < W ? wp : 2 * (W - 1) - wp;
-  T* o = out + idx * pitch;
+  // destination pixel inside an optionally zero-bordered buffer [B][img_rows][row_pix][pitch]
+  T* o = out + (((long long)b * img_rows + hp + pad_top) * row_pix + wp + pad_left) * pitch;
   for (int c = 0; c < C; ++c) {
     long long s = (((long long)b * C + c) * H + h) * W + w;
     float xv = xt[s];
@@ -39,15 +41,17 @@ __global__ void prep_input_kernel(const float* __restrict__ xt, const float* __r
 
 template <typename T>
 void launch_prep_input(const float* xt, const float* cond, T* out, int B, int C, int H, int W, int Hp, int Wp,
-                       int out_pitch, int conditional, cudaStream_t st) {
+                       int out_pitch, int conditional, cudaStream_t st, int pad_top, int pad_left, int row_pix,
+                       int img_rows) {
   long long total = (long long)B * Hp * Wp;
+  if (row_pix == 0) { row_pix = Wp; img_rows = Hp; }
   prep_input_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xt, cond, out, B, C, H, W, Hp, Wp, out_pitch,
-                                                                         conditional);
+                                                                         conditional, pad_top, pad_left, row_pix, img_rows);
 }
 template void launch_prep_input<float>(const float*, const float*, float*, int, int, int, int, int, int, int, int,
-                                       cudaStream_t);
+                                       cudaStream_t, int, int, int, int);
 template void launch_prep_input<bf16>(const float*, const float*, bf16*, int, int, int, int, int, int, int, int,
-                                      cudaStream_t);
+                                      cudaStream_t, int, int, int, int);
 
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int C, int H, int W,
@@ -85,272 +89,6 @@ void launch_nhwc_to_nchw(const T* in, int in_pitch, float* out, int B, int C, in
 }
 template void launch_nhwc_to_nchw<float>(const float*, int, float*, int, int, int, int, cudaStream_t);
 template void launch_nhwc_to_nchw<bf16>(const bf16*, int, float*, int, int, int, int, cudaStream_t);
-
-// =============================================================================================
-// channel LayerNorm: (x-mean)*rsqrt(var_biased+1e-5)*g (+ residual)   module_util.py:70-79,20-26
-// one warp per pixel, two-pass statistics (matches torch.var(unbiased=False) numerics closely)
-// =============================================================================================
-template <typename T>
-__global__ void layernorm_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
-                                 const T* __restrict__ res, int res_pitch, T* __restrict__ out, int out_pitch,
-                                 long long npix, int C) {
-  int lane = threadIdx.x & 31;
-  long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (pix >= npix) return;
-  const T* xr = x + pix * x_pitch;
-  float s = 0.f;
-  for (int c = lane; c < C; c += 32) s += to_f(xr[c]);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  float mean = s / (float)C;
-  float v = 0.f;
-  for (int c = lane; c < C; c += 32) {
-    float d = to_f(xr[c]) - mean;
-    v += d * d;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  float rstd = 1.0f / sqrtf(v / (float)C + 1e-5f);
-  T* orow = out + pix * out_pitch;
-  const T* rr = res ? res + pix * res_pitch : nullptr;
-  for (int c = lane; c < C; c += 32) {
-    float y = (to_f(xr[c]) - mean) * rstd * g[c];
-    if (rr) y += to_f(rr[c]);
-    orow[c] = from_f<T>(y);
-  }
-}
-template <typename T>
-void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int res_pitch, T* out, int out_pitch,
-                      long long npix, int C, cudaStream_t st) {
-  const int warps = 8;
-  layernorm_kernel<T><<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch, out,
-                                                                                     out_pitch, npix, C);
-}
-template void launch_layernorm<float>(const float*, int, const float*, const float*, int, float*, int, long long, int,
-                                      cudaStream_t);
-template void launch_layernorm<bf16>(const bf16*, int, const float*, const bf16*, int, bf16*, int, long long, int,
-                                     cudaStream_t);
-
-// =============================================================================================
-// LinearAttention core (module_util.py:163-177).  heads=4, dim_head=32 (fixed by the reference).
-// qkv channel layout: [q(4x32) | k(4x32) | v(4x32)], head h = channels h*32..h*32+31 of each third.
-//   pass A: per (b,h,chunk): m[d]=max_n k, s[d]=sum_n exp(k-m), c[d][e]=sum_n exp(k-m) v[e]
-//   pass B: combine chunks, ctx[d][e] = c/s/N
-//   pass C: per pixel/head: q=softmax_d(q)*32^-.5 ; out[e] = sum_d ctx[d][e] q[d]
-// =============================================================================================
-static const int LA_CH = 128;      // pixels per chunk
-static const int LA_REC = 64 + 1024;  // floats per partial record
-
-size_t linattn_partial_floats(int B, int N) { return (size_t)B * 4 * ((N + LA_CH - 1) / LA_CH) * LA_REC; }
-
-template <typename T>
-__global__ void __launch_bounds__(256) la_partial_kernel(const T* __restrict__ qkv, int pitch, float* __restrict__ part,
-                                                         int N, int nchunks) {
-  __shared__ float ks[LA_CH][33];
-  __shared__ __align__(16) float vs[LA_CH][32];
-  __shared__ float ms[32], ss[32];
-  int chunk = blockIdx.x, bh = blockIdx.y;
-  int b = bh >> 2, h = bh & 3;
-  int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  int n0 = chunk * LA_CH;
-  for (int i = tid; i < LA_CH * 32; i += 256) {
-    int n = i >> 5, d = i & 31;
-    float kv = -INFINITY, vv = 0.f;
-    if (n0 + n < N) {
-      const T* row = qkv + ((long long)b * N + n0 + n) * pitch;
-      kv = to_f(row[128 + h * 32 + d]);
-      vv = to_f(row[256 + h * 32 + d]);
-    }
-    ks[n][d] = kv;
-    vs[n][d] = vv;
-  }
-  __syncthreads();
-  for (int d = warp * 4; d < warp * 4 + 4; ++d) {
-    float m = -INFINITY;
-    for (int n = lane; n < LA_CH; n += 32) m = fmaxf(m, ks[n][d]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float s = 0.f;
-    for (int n = lane; n < LA_CH; n += 32) {
-      float p = expf(ks[n][d] - m);
-      ks[n][d] = p;
-      s += p;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) {
-      ms[d] = m;
-      ss[d] = s;
-    }
-  }
-  __syncthreads();
-  int d = tid >> 3, e0 = (tid & 7) * 4;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  for (int n = 0; n < LA_CH; ++n) {
-    float p = ks[n][d];
-    float4 v = *reinterpret_cast<const float4*>(&vs[n][e0]);
-    a0 += p * v.x;
-    a1 += p * v.y;
-    a2 += p * v.z;
-    a3 += p * v.w;
-  }
-  float* rec = part + ((long long)bh * nchunks + chunk) * LA_REC;
-  if (tid < 32) {
-    rec[tid] = ms[tid];
-    rec[32 + tid] = ss[tid];
-  }
-  *reinterpret_cast<float4*>(rec + 64 + d * 32 + e0) = make_float4(a0, a1, a2, a3);
-}
-
-__global__ void __launch_bounds__(1024) la_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx,
-                                                          int N, int nchunks) {
-  int bh = blockIdx.x, tid = threadIdx.x;
-  int d = tid >> 5;
-  const float* base = part + (long long)bh * nchunks * LA_REC;
-  float M = -INFINITY;
-  for (int c = 0; c < nchunks; ++c) M = fmaxf(M, base[(long long)c * LA_REC + d]);
-  float S = 0.f, acc = 0.f;
-  for (int c = 0; c < nchunks; ++c) {
-    const float* rec = base + (long long)c * LA_REC;
-    float w = expf(rec[d] - M);
-    S += rec[32 + d] * w;
-    acc += rec[64 + tid] * w;
-  }
-  ctx[(long long)bh * 1024 + tid] = acc / S / (float)N;
-}
-
-template <typename T>
-__global__ void __launch_bounds__(256) la_out_kernel(const T* __restrict__ qkv, int pitch, const float* __restrict__ ctx,
-                                                     T* __restrict__ hidden, int hid_pitch, int N) {
-  __shared__ __align__(16) float cs[4][32][32];
-  int b = blockIdx.y, tid = threadIdx.x;
-  for (int i = tid; i < 4096; i += 256) (&cs[0][0][0])[i] = ctx[(long long)b * 4096 + i];
-  __syncthreads();
-  int h = tid >> 6;
-  int n = blockIdx.x * 64 + (tid & 63);
-  if (n >= N) return;
-  const T* row = qkv + ((long long)b * N + n) * pitch + h * 32;
-  float q[32];
-  float m = -INFINITY;
-#pragma unroll
-  for (int d = 0; d < 32; ++d) {
-    q[d] = to_f(row[d]);
-    m = fmaxf(m, q[d]);
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int d = 0; d < 32; ++d) {
-    q[d] = expf(q[d] - m);
-    s += q[d];
-  }
-  const float scale = 0.17677669529663687f;  // 32^-0.5
-#pragma unroll
-  for (int d = 0; d < 32; ++d) q[d] = q[d] / s * scale;
-  float o[32];
-#pragma unroll
-  for (int e = 0; e < 32; ++e) o[e] = 0.f;
-#pragma unroll
-  for (int d = 0; d < 32; ++d) {
-#pragma unroll
-    for (int e = 0; e < 32; e += 4) {
-      float4 c = *reinterpret_cast<const float4*>(&cs[h][d][e]);
-      o[e] += c.x * q[d];
-      o[e + 1] += c.y * q[d];
-      o[e + 2] += c.z * q[d];
-      o[e + 3] += c.w * q[d];
-    }
-  }
-  T* orow = hidden + ((long long)b * N + n) * hid_pitch + h * 32;
-#pragma unroll
-  for (int e = 0; e < 32; ++e) orow[e] = from_f<T>(o[e]);
-}
-
-template <typename T>
-void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
-                    cudaStream_t st) {
-  int nchunks = (N + LA_CH - 1) / LA_CH;
-  la_partial_kernel<T><<<dim3(nchunks, B * 4), 256, 0, st>>>(qkv, qkv_pitch, partial, N, nchunks);
-  la_combine_kernel<<<B * 4, 1024, 0, st>>>(partial, ctx, N, nchunks);
-  la_out_kernel<T><<<dim3((N + 63) / 64, B), 256, 0, st>>>(qkv, qkv_pitch, ctx, hidden, hid_pitch, N);
-}
-template void launch_linattn<float>(const float*, int, float*, float*, float*, int, int, int, cudaStream_t);
-template void launch_linattn<bf16>(const bf16*, int, float*, float*, bf16*, int, int, int, cudaStream_t);
-
-// =============================================================================================
-// full softmax attention (module_util.py:192-204) - denoising-sde mid_attn only.
-// thread per query, keys/values staged through shared memory, online softmax.
-// =============================================================================================
-template <typename T>
-__global__ void __launch_bounds__(128) fullattn_kernel(const T* __restrict__ qkv, int pitch, T* __restrict__ hidden,
-                                                       int hid_pitch, int N) {
-  __shared__ __align__(16) float ks[64][32];
-  __shared__ __align__(16) float vs[64][32];
-  int bh = blockIdx.y, b = bh >> 2, h = bh & 3;
-  int tid = threadIdx.x;
-  int i = blockIdx.x * 128 + tid;
-  bool valid = i < N;
-  float q[32], acc[32];
-  const float scale = 0.17677669529663687f;
-  if (valid) {
-    const T* row = qkv + ((long long)b * N + i) * pitch + h * 32;
-#pragma unroll
-    for (int d = 0; d < 32; ++d) q[d] = to_f(row[d]) * scale;
-  } else {
-#pragma unroll
-    for (int d = 0; d < 32; ++d) q[d] = 0.f;
-  }
-#pragma unroll
-  for (int d = 0; d < 32; ++d) acc[d] = 0.f;
-  float m = -INFINITY, l = 0.f;
-  for (int j0 = 0; j0 < N; j0 += 64) {
-    __syncthreads();
-    for (int t = tid; t < 64 * 32; t += 128) {
-      int j = t >> 5, d = t & 31;
-      float kv = 0.f, vv = 0.f;
-      if (j0 + j < N) {
-        const T* row = qkv + ((long long)b * N + j0 + j) * pitch;
-        kv = to_f(row[128 + h * 32 + d]);
-        vv = to_f(row[256 + h * 32 + d]);
-      }
-      ks[j][d] = kv;
-      vs[j][d] = vv;
-    }
-    __syncthreads();
-    int jmax = min(64, N - j0);
-    for (int j = 0; j < jmax; ++j) {
-      float s = 0.f;
-#pragma unroll
-      for (int d = 0; d < 32; d += 4) {
-        float4 k4 = *reinterpret_cast<const float4*>(&ks[j][d]);
-        s += q[d] * k4.x + q[d + 1] * k4.y + q[d + 2] * k4.z + q[d + 3] * k4.w;
-      }
-      float mn = fmaxf(m, s);
-      float alpha = expf(m - mn);
-      float p = expf(s - mn);
-      l = l * alpha + p;
-#pragma unroll
-      for (int d = 0; d < 32; d += 4) {
-        float4 v4 = *reinterpret_cast<const float4*>(&vs[j][d]);
-        acc[d] = acc[d] * alpha + p * v4.x;
-        acc[d + 1] = acc[d + 1] * alpha + p * v4.y;
-        acc[d + 2] = acc[d + 2] * alpha + p * v4.z;
-        acc[d + 3] = acc[d + 3] * alpha + p * v4.w;
-      }
-      m = mn;
-    }
-  }
-  if (valid) {
-    T* orow = hidden + ((long long)b * N + i) * hid_pitch + h * 32;
-#pragma unroll
-    for (int d = 0; d < 32; ++d) orow[d] = from_f<T>(acc[d] / l);
-  }
-}
-template <typename T>
-void launch_fullattn(const T* qkv, int qkv_pitch, T* hidden, int hid_pitch, int B, int N, cudaStream_t st) {
-  fullattn_kernel<T><<<dim3((N + 127) / 128, B * 4), 128, 0, st>>>(qkv, qkv_pitch, hidden, hid_pitch, N);
-}
-template void launch_fullattn<float>(const float*, int, float*, int, int, int, cudaStream_t);
-template void launch_fullattn<bf16>(const bf16*, int, bf16*, int, int, int, cudaStream_t);
 
 // =============================================================================================
 // timestep embedding -> per-ResBlock (scale, shift) table

@@ -41,11 +41,17 @@ struct RunCfg {  // per-invocation pointers read by the op closures at launch ti
 
 struct Plan;
 typedef std::function<void(Plan*, cudaStream_t)> Op;
+enum { CAT_TC = 0, CAT_SIMT, CAT_LN, CAT_ATTN, CAT_MISC, CAT_UPDATE, CAT_COUNT };
+struct OpRec {
+  int cat;
+  double flops;  // executed multiply-add flops (2*MAC) of this op, 0 for memory-bound ops
+  Op fn;
+};
 
 struct Plan {
   int B, H, W, Hp, Wp;
   std::vector<void*> allocs;
-  std::vector<Op> ops;
+  std::vector<OpRec> ops;
   std::vector<TcConvDesc*> tc_descs;
   RunCfg cur;
   // chain state
@@ -81,6 +87,9 @@ struct irsde_ctx {
   long long dev_bytes = 0;
   std::vector<void*> allocs;
   bool tc_ok = false;
+  bool prof = false;
+  struct ProfEv { int cat; double flops; cudaEvent_t e0, e1; };
+  std::vector<ProfEv> prof_events;
   bool use_tc = false;  // bf16 mode: route eligible convs through the tcgen05 engine
 };
 
@@ -156,6 +165,31 @@ __global__ void pack_tc_up_kernel(const float* __restrict__ w, bf16* __restrict_
   for (int r = r0; r <= r1; ++r)
     for (int s = s0; s <= s1; ++s) acc += w[(((long long)co * Cin + c) * 3 + r) * 3 + s];
   o[idx] = __float2bfloat16_rn(acc);
+}
+
+// 7x7 stem as 7 row-taps with K=64 = 8 pixels x 8 channels (see conv_tc.cu): [r][Cout][s*8+c]
+__global__ void pack_tc_stem_kernel(const float* __restrict__ w, bf16* __restrict__ o, int Cout, int Cin) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)7 * Cout * 64;
+  if (idx >= total) return;
+  int j = idx % 64;
+  int co = (idx / 64) % Cout;
+  int r = idx / ((long long)64 * Cout);
+  int s = j >> 3, c = j & 7;
+  float v = (s < 7 && c < Cin) ? w[(((long long)co * Cin + c) * 7 + r) * 7 + s] : 0.f;
+  o[idx] = __float2bfloat16_rn(v);
+}
+// [tap][Cout_pad][Cin] with zero rows for co >= Cout (head conv, Cout=3)
+__global__ void pack_tc_padded_kernel(const float* __restrict__ w, bf16* __restrict__ o, int Cout, int Cout_pad, int Cin,
+                                      int KH, int KW) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Cout_pad * Cin * KH * KW;
+  if (idx >= total) return;
+  int c = idx % Cin;
+  int co = (idx / Cin) % Cout_pad;
+  int tap = idx / ((long long)Cout_pad * Cin);
+  int r = tap / KW, s = tap % KW;
+  o[idx] = __float2bfloat16_rn(co < Cout ? w[(((long long)co * Cin + c) * KH + r) * KW + s] : 0.f);
 }
 
 // ---- architecture description --------------------------------------------------------------------
@@ -257,6 +291,7 @@ struct Builder {
   std::string err;
   std::multimap<size_t, void*> free_tmp;
   std::map<void*, size_t> tmp_size;
+  bool stem_padded = false;  // X0 lives in the zero-bordered [B][Hp+6][Wp+8][8] layout of the tcgen05 stem
 
   T* alloc(long long elems) {
     void* p = dev_alloc(ctx, (size_t)elems * sizeof(T), &plan->allocs);
@@ -294,6 +329,9 @@ struct Builder {
     g.Hout = (Hin * up + 2 * pad - K) / stride + 1;
     g.Wout = (Win * up + 2 * pad - K) / stride + 1;
     g.Cout = Cout;
+    double simt_flops = 2.0 * plan->B * g.Hout * g.Wout * (double)Cout * in.C * K * K;
+    // the tensor-core engine runs nearest-x2 + 3x3 as four 2x2 phase convolutions: 4 taps per output pixel
+    double tc_flops = (K == 3 && up == 2) ? simt_flops * 4.0 / 9.0 : simt_flops;
     Epilogue ep;
     memset(&ep, 0, sizeof ep);
     ep.bias = bias ? fw(bias) : nullptr;
@@ -307,7 +345,26 @@ struct Builder {
     if constexpr (std::is_same<T, bf16>::value) {
       bool shape_ok = (K == 3 && stride == 1 && pad == 1) || (K == 1 && stride == 1 && pad == 0 && up == 1) ||
                       (K == 4 && stride == 2 && pad == 1 && up == 1 && Hin % 2 == 0 && Win % 2 == 0);
-      if (ctx->use_tc && !nchw && shape_ok && in.C % 8 == 0 && Cout % 8 == 0 && in.pitch % 8 == 0 && out.pitch % 8 == 0) {
+      bool stem_tc = ctx->use_tc && stem_padded && K == 7 && Cout % 8 == 0 && out.pitch % 8 == 0;
+      if (stem_tc) {
+        const bf16* wt = ctx->w_tc[wname];
+        if (!wt) { ok = false; err = "unpacked tc weight " + wname; return; }
+        TcTap taps[16];
+        for (int r = 0; r < 7; ++r) taps[r] = TcTap{r, 0, 0};
+        std::string terr;
+        TcConvDesc* d = tc_conv_create(in.p, 8, plan->B, Hin, Win, 64, -1, wt, Cout, 7, taps, 1, ep, out.p, out.pitch, g.Hout,
+                                       g.Wout, &terr);
+        if (!d) { ok = false; err = "tc_conv_create(stem): " + terr; return; }
+        plan->tc_descs.push_back(d);
+        double fl = 2.0 * plan->B * g.Hout * g.Wout * (double)Cout * 448;
+        plan->ops.push_back(OpRec{CAT_TC, fl, [=](Plan*, cudaStream_t st) {
+          tc_conv_launch(d, st);
+          c->launches++;
+        }});
+        return;
+      }
+      if (ctx->use_tc && shape_ok && in.C % 8 == 0 && in.pitch % 8 == 0 &&
+          (nchw ? (K == 3 && up == 1) : (Cout % 8 == 0 && out.pitch % 8 == 0))) {
         const bf16* wt = ctx->w_tc[wname];
         if (!wt) { ok = false; err = "unpacked tc weight " + wname; return; }
         TcTap taps[16];
@@ -326,10 +383,10 @@ struct Builder {
           planes = 4; Ha = Hin / 2; Wa = Win / 2; a_pitch = in.C;
           bf16* s2d = tmp((long long)plan->B * Hin * Win * in.C);
           int Bc = plan->B, Cc = in.C;
-          plan->ops.push_back([=](Plan*, cudaStream_t st) {
+          plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
             launch_space_to_depth<bf16>(in.p, in.pitch, s2d, Bc, Hin, Win, Cc, st);
             c->launches++;
-          });
+          }});
           a_ptr = s2d;
           release(s2d);  // safe: stream order; the next tmp user runs after this conv
         }
@@ -338,23 +395,25 @@ struct Builder {
                                        out.pitch, g.Hout, g.Wout, &terr);
         if (!d) { ok = false; err = "tc_conv_create(" + wname + "): " + terr; return; }
         plan->tc_descs.push_back(d);
-        plan->ops.push_back([=](Plan* p, cudaStream_t st) {
+        int cH = plan->H, cW = plan->W;
+        plan->ops.push_back(OpRec{CAT_TC, tc_flops, [=](Plan* p, cudaStream_t st) {
           if (use_ss) tc_conv_set_runtime(d, p->cur.ss, p->cur.t_ptr, p->cur.ss_img_stride);
+          if (nchw) tc_conv_set_out_nchw(d, p->cur.out, cH, cW);
           tc_conv_launch(d, st);
           c->launches++;
-        });
+        }});
         return;
       }
     }
     const float* w = ctx->w_simt[wname];
     if (!w) { ok = false; err = "unpacked weight " + wname; return; }
     int H = plan->H, Wd = plan->W;
-    plan->ops.push_back([=](Plan* p, cudaStream_t st) {
+    plan->ops.push_back(OpRec{CAT_SIMT, simt_flops, [=](Plan* p, cudaStream_t st) {
       Epilogue e = ep;
       if (use_ss) { e.ss = p->cur.ss; e.t_ptr = p->cur.t_ptr; e.ss_img_stride = p->cur.ss_img_stride; }
       launch_conv_simt<T>(g, in.p, in.pitch, w, e, out.p, out.pitch, nchw ? p->cur.out : nullptr, H, Wd, st);
       c->launches++;
-    });
+    }});
   }
 
   void resblock(const std::string& pre, V in, int Cout, V out, int H, int W) {
@@ -381,34 +440,34 @@ struct Builder {
     T* xn = tmp(npix * C);
     float* g1 = fw(pre + "fn.norm.g");
     irsde_ctx* c = ctx;
-    plan->ops.push_back([=](Plan*, cudaStream_t st) {
+    plan->ops.push_back(OpRec{CAT_LN, 0.0, [=](Plan*, cudaStream_t st) {
       launch_layernorm<T>(in.p, in.pitch, g1, nullptr, 0, xn, C, npix, C, st);
       c->launches++;
-    });
+    }});
     T* qkv = tmp(npix * 384);
     conv(pre + "fn.fn.to_qkv.weight", V{xn, C, C}, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384);
     release(xn);
     T* hid = tmp(npix * 128);
     if (full) {
-      plan->ops.push_back([=](Plan*, cudaStream_t st) {
+      plan->ops.push_back(OpRec{CAT_ATTN, 0.0, [=](Plan*, cudaStream_t st) {
         launch_fullattn<T>(qkv, 384, hid, 128, B, N, st);
         c->launches++;
-      });
+      }});
       std::string bn = pre + "fn.fn.to_out.bias";
       conv(pre + "fn.fn.to_out.weight", V{hid, 128, 128}, H, W, 1, 1, 0, 1, bn.c_str(), "", 0, &in, out, C);
     } else {
-      plan->ops.push_back([=](Plan*, cudaStream_t st) {
+      plan->ops.push_back(OpRec{CAT_ATTN, 0.0, [=](Plan*, cudaStream_t st) {
         launch_linattn<T>(qkv, 384, la_partial, la_ctx, hid, 128, B, N, st);
         c->launches += 3;
-      });
+      }});
       T* y = tmp(npix * C);
       std::string bn = pre + "fn.fn.to_out.0.bias";
       conv(pre + "fn.fn.to_out.0.weight", V{hid, 128, 128}, H, W, 1, 1, 0, 1, bn.c_str(), "", 0, nullptr, V{y, C, C}, C);
       float* g2 = fw(pre + "fn.fn.to_out.1.g");
-      plan->ops.push_back([=](Plan*, cudaStream_t st) {
+      plan->ops.push_back(OpRec{CAT_LN, 0.0, [=](Plan*, cudaStream_t st) {
         launch_layernorm<T>(y, C, g2, in.p, in.pitch, out.p, out.pitch, npix, C, st);
         c->launches++;
-      });
+      }});
       release(y);
     }
     release(qkv);
@@ -433,14 +492,19 @@ struct Builder {
     float* la_ctx = (float*)dev_alloc(ctx, (size_t)B * 4096 * sizeof(float), &plan->allocs);
     if (!la_partial || !la_ctx) { ok = false; err = "cudaMalloc failed"; return; }
 
-    T* X0 = alloc(np0 * pitch0);
-    T* F = alloc(np0 * 2 * nf);
     int in_nc = c.in_nc, Hh = plan->H, Ww = plan->W, Hp = plan->Hp, Wp = plan->Wp;
+    stem_padded = std::is_same<T, bf16>::value && ctx->use_tc && pitch0 == 8 && nf % 8 == 0;
+    long long x0_elems = stem_padded ? (long long)B * (Hp + 6) * (Wp + 8) * 8 + 64 : np0 * pitch0;
+    T* X0 = alloc(x0_elems);
+    if (X0 && stem_padded) cudaMemset(X0, 0, (size_t)x0_elems * sizeof(T));  // borders stay zero forever
+    T* F = alloc(np0 * 2 * nf);
     irsde_ctx* cx = ctx;
-    plan->ops.push_back([=](Plan* p, cudaStream_t st) {
-      launch_prep_input<T>(p->cur.x, p->cur.mu, X0, B, in_nc, Hh, Ww, Hp, Wp, pitch0, cond ? 1 : 0, st);
+    bool sp = stem_padded;
+    plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan* p, cudaStream_t st) {
+      if (sp) launch_prep_input<T>(p->cur.x, p->cur.mu, X0, B, in_nc, Hh, Ww, Hp, Wp, pitch0, cond ? 1 : 0, st, 3, 3, Wp + 8, Hp + 6);
+      else launch_prep_input<T>(p->cur.x, p->cur.mu, X0, B, in_nc, Hh, Ww, Hp, Wp, pitch0, cond ? 1 : 0, st);
       cx->launches++;
-    });
+    }});
     conv("init_conv.weight", V{X0, pitch0, C0}, hs[0], ws[0], 7, 1, 3, 1, nullptr, "", 0, nullptr, view(F, 2 * nf, nf, nf), nf);
     V cur = view(F, 2 * nf, nf, nf);
     std::vector<T*> U1(depth), U2(depth);
@@ -553,7 +617,19 @@ int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
 }
 
 void run_forward(irsde_ctx* ctx, Plan* p, cudaStream_t st) {
-  for (auto& op : p->ops) op(p, st);
+  if (!ctx->prof) {
+    for (auto& op : p->ops) op.fn(p, st);
+    return;
+  }
+  for (auto& op : p->ops) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    cudaEventRecord(e0, st);
+    op.fn(p, st);
+    cudaEventRecord(e1, st);
+    ctx->prof_events.push_back({op.cat, op.flops, e0, e1});
+  }
 }
 
 // default per-timestep scalars in fp32, same op order as the reference's 0-dim tensor math
@@ -728,12 +804,18 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
     pack_simt_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, ws, Cout, Cin, KH, KW);
     if (ctx->cfg.precision == IRSDE_PREC_BF16) {
       bool is_up = s.name.find(".3.1.weight") != std::string::npos;
-      long long nt = is_up ? (long long)16 * Cout * Cin : n;
+      bool is_stem = s.name == "init_conv.weight";
+      int Cout_pad = (Cout + 7) / 8 * 8;
+      long long nt = is_up ? (long long)16 * Cout * Cin : (is_stem ? (long long)7 * Cout * 64 : (long long)Cout_pad * Cin * KH * KW);
       bf16*& wt = ctx->w_tc[s.name];
       if (!wt) wt = (bf16*)dev_alloc(ctx, (size_t)nt * 2, &ctx->allocs);
       if (!wt) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
       if (is_up)
         pack_tc_up_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cin);
+      else if (is_stem && Cin <= 8)
+        pack_tc_stem_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cin);
+      else if (Cout_pad != Cout)
+        pack_tc_padded_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cout_pad, Cin, KH, KW);
       else
         pack_tc_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cin, KH, KW);
     }
@@ -860,7 +942,7 @@ int irsde_reverse(irsde_ctx* ctx, int32_t mode, const float* xT, const float* mu
     launch_advance_step(p->d_step, s);
     ctx->launches += 2;
   };
-  if (use_graph) {
+  if (use_graph && !ctx->prof) {
     if (!p->graph[mode]) {
       cudaStream_t cs;
       CUDA_TRY(ctx, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
@@ -902,6 +984,33 @@ int irsde_noise_state(irsde_ctx* ctx, const float* mu, float* out, int64_t n, ui
   return IRSDE_OK;
 }
 
+int irsde_profile_begin(irsde_ctx* ctx) {
+  if (!ctx) return fail(nullptr, IRSDE_ERR_INVALID, "null ctx");
+  for (auto& e : ctx->prof_events) { cudaEventDestroy(e.e0); cudaEventDestroy(e.e1); }
+  ctx->prof_events.clear();
+  ctx->prof = true;
+  return IRSDE_OK;
+}
+
+int irsde_profile_end(irsde_ctx* ctx, double* ms, double* flops, int64_t* launches, int32_t ncat) {
+  if (!ctx || !ms || !flops || !launches || ncat < CAT_COUNT) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  cudaSetDevice(ctx->cfg.device);
+  ctx->prof = false;
+  CUDA_TRY(ctx, cudaDeviceSynchronize());
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  for (auto& e : ctx->prof_events) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, e.e0, e.e1);
+    ms[e.cat] += t;
+    flops[e.cat] += e.flops;
+    launches[e.cat] += 1;
+    cudaEventDestroy(e.e0);
+    cudaEventDestroy(e.e1);
+  }
+  ctx->prof_events.clear();
+  return IRSDE_OK;
+}
+
 int64_t irsde_launch_count(const irsde_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t irsde_device_bytes(const irsde_ctx* ctx) { return ctx ? ctx->dev_bytes : 0; }
 
@@ -917,12 +1026,17 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
     std::string terr;
     if (!tc_init(&terr)) return fail(ctx, IRSDE_ERR_CUDA, "tc_init: " + terr);
     bool k3 = KH == 3 && KW == 3 && stride == 1 && pad == 1, k1 = KH == 1 && KW == 1 && stride == 1 && pad == 0 && up == 1,
-         k4 = KH == 4 && KW == 4 && stride == 2 && pad == 1 && up == 1 && H % 2 == 0 && W % 2 == 0;
-    if (!(k3 || k1 || k4) || Cin % 8 || Cout % 8) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "shape not supported by the tensor-core engine");
+         k4 = KH == 4 && KW == 4 && stride == 2 && pad == 1 && up == 1 && H % 2 == 0 && W % 2 == 0,
+         k7 = KH == 7 && KW == 7 && stride == 1 && pad == 3 && up == 1 && Cin <= 8 && Cout % 8 == 0;
+    bool nchw = Cout % 8 != 0;  // head-style output: fp32 NCHW straight from the epilogue
+    if (!(k3 || k1 || k4 || k7) || (!k7 && Cin % 8) || (nchw && !(k3 && up == 1)))
+      return fail(ctx, IRSDE_ERR_UNSUPPORTED, "shape not supported by the tensor-core engine");
     int Ho = (H * up + 2 * pad - KH) / stride + 1, Wo = (W * up + 2 * pad - KW) / stride + 1;
+    int Cout_pad = (Cout + 7) / 8 * 8;
     std::vector<void*> tmp;
-    long long nin = (long long)B * H * W * Cin, nw = (long long)Cout * Cin * KH * KW, nout = (long long)B * Ho * Wo * Cout;
-    long long nwt = (k3 && up == 2) ? (long long)16 * Cout * Cin : nw;
+    long long nin = k7 ? (long long)B * (H + 6) * (W + 8) * 8 + 64 : (long long)B * H * W * Cin;
+    long long nw = (long long)Cout * Cin * KH * KW, nout = (long long)B * Ho * Wo * Cout_pad;
+    long long nwt = (k3 && up == 2) ? (long long)16 * Cout * Cin : (k7 ? (long long)7 * Cout * 64 : (long long)Cout_pad * Cin * KH * KW);
     bf16* xin = (bf16*)dev_alloc(ctx, nin * 2, &tmp);
     bf16* xs2d = (bf16*)dev_alloc(ctx, nin * 2, &tmp);
     bf16* wp = (bf16*)dev_alloc(ctx, nwt * 2, &tmp);
@@ -931,13 +1045,20 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
     TcConvDesc* d = nullptr;
     if (!xin || !xs2d || !wp || !yo) rc = fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
     if (!rc) {
-      launch_nchw_to_nhwc<bf16>(x, xin, B, Cin, H, W, Cin, st);
-      if (k3 && up == 2) pack_tc_up_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin);
-      else pack_tc_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin, KH, KW);
+      if (k7) {
+        cudaMemsetAsync(xin, 0, nin * 2, st);
+        launch_prep_input<bf16>(x, nullptr, xin, B, Cin, H, W, H, W, 8, 0, st, 3, 3, W + 8, H + 6);
+        pack_tc_stem_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin);
+      } else {
+        launch_nchw_to_nhwc<bf16>(x, xin, B, Cin, H, W, Cin, st);
+        if (k3 && up == 2) pack_tc_up_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin);
+        else pack_tc_padded_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cout_pad, Cin, KH, KW);
+      }
       TcTap taps[16];
-      int ntaps = 0, nph = 1, planes = 1, Ha = H, Wa = W;
+      int ntaps = 0, nph = 1, planes = 1, Ha = H, Wa = W, Ca = Cin, a_pitch = Cin;
       const bf16* a_ptr = xin;
-      if (k3 && up == 1) { for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) taps[ntaps++] = TcTap{r - 1, q - 1, 0}; }
+      if (k7) { for (int r = 0; r < 7; ++r) taps[ntaps++] = TcTap{r, 0, 0}; planes = -1; Ca = 64; a_pitch = 8; }
+      else if (k3 && up == 1) { for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) taps[ntaps++] = TcTap{r - 1, q - 1, 0}; }
       else if (k3) { nph = 4; for (int a = 0; a < 2; ++a) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{a - 1, q - 1, 0}; }
       else if (k1) { taps[ntaps++] = TcTap{0, 0, 0}; }
       else {
@@ -951,12 +1072,13 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
       memset(&ep, 0, sizeof ep);
       ep.bias = bias;
       ep.silu = silu;
-      d = tc_conv_create(a_ptr, Cin, B, Ha, Wa, Cin, planes, wp, Cout, ntaps, taps, nph, ep, yo, Cout, Ho, Wo, &terr);
+      d = tc_conv_create(a_ptr, a_pitch, B, Ha, Wa, Ca, planes, wp, Cout, ntaps, taps, nph, ep, nchw ? nullptr : yo, Cout, Ho, Wo, &terr);
       if (!d) rc = fail(ctx, IRSDE_ERR_INVALID, "tc_conv_create: " + terr);
     }
     if (!rc) {
+      if (nchw) tc_conv_set_out_nchw(d, y, Ho, Wo);
       tc_conv_launch(d, st);
-      launch_nhwc_to_nchw<bf16>(yo, Cout, y, B, Cout, Ho, Wo, st);
+      if (!nchw) launch_nhwc_to_nchw<bf16>(yo, Cout, y, B, Cout, Ho, Wo, st);
       ctx->launches += 4;
       cudaError_t e = cudaStreamSynchronize(st);
       if (e == cudaSuccess) e = cudaGetLastError();

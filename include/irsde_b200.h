@@ -106,6 +106,13 @@ int irsde_reverse(irsde_ctx* ctx, int32_t mode, const float* xT, const float* mu
 /* x_T = mu + N(0,1)*max_sigma on the device (sde_utils.py:360-361) with the library's Philox. */
 int irsde_noise_state(irsde_ctx* ctx, const float* mu, float* out, int64_t n, uint64_t seed, void* stream);
 
+/* Instrumented pass: between begin/end every op of the launch plan is bracketed by CUDA events on the
+ * launching stream (graph replay is bypassed).  end() synchronises and returns, per op category
+ * (0 tcgen05 conv, 1 SIMT conv, 2 LayerNorm, 3 attention, 4 misc, 5 update), the summed device time in
+ * ms, the executed conv flops and the number of ops.  ncat must be >= 6. */
+int irsde_profile_begin(irsde_ctx* ctx);
+int irsde_profile_end(irsde_ctx* ctx, double* ms, double* flops, int64_t* launches, int32_t ncat);
+
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t irsde_launch_count(const irsde_ctx* ctx);
 /* Bytes of device memory held by the context (weights + workspaces). */

@@ -246,6 +246,9 @@ TC_CASES = [
     (2, 64, 16, 24, 128, 4, 2, 1, False, True, False),   # downsample over space-to-depth planes
     (2, 128, 8, 12, 64, 3, 1, 1, True, True, False),     # upsample phases with pre-summed weights
     (1, 8, 20, 28, 384, 1, 1, 0, False, False, False),   # to_qkv at nf=8: tiny K, 2 N tiles
+    (2, 6, 20, 28, 64, 7, 1, 3, False, False, False),    # 7x7 stem as 7 row-taps (overlapping-stride TMA view)
+    (1, 3, 9, 13, 16, 7, 1, 3, False, False, False),     # stem of the denoising variant (Cin=3), ragged size
+    (2, 64, 16, 24, 3, 3, 1, 1, False, True, False),     # head: Cout=3, fp32 NCHW straight from the epilogue
 ]
 
 
