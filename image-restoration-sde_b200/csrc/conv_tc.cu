@@ -18,6 +18,7 @@
 // Two CTAs are co-resident per SM for BN<=128 so one CTA's epilogue overlaps the other's main loop.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -329,6 +330,231 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
   }
 }
 
+// =====================================================================================================
+// Persistent variant (default): one CTA per SM loops over output tiles.  The TMEM accumulator is
+// double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMA main loop of tile i+1,
+// the smem ring is as deep as 192 KB allows (BN=256: 4, BN=128: 6, BN<=64: 8 stages) to cover TMA
+// latency, and the prologue (barrier init, TMEM alloc, descriptor prefetch) is paid once per SM.
+// =====================================================================================================
+template <int BN>
+struct TcCfgP {
+  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  static constexpr int EPI_FLOATS = 3 * BN;
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 256;
+  static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+struct TileCoord {
+  int b, phase, py, px, h0, w0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, int tiles_m, int BN) {
+  TileCoord t;
+  int m_idx = tile % tiles_m;
+  t.n0 = (tile / tiles_m) * BN;
+  const int tw_i = m_idx % P.tilesW; m_idx /= P.tilesW;
+  const int th_i = m_idx % P.tilesH; m_idx /= P.tilesH;
+  t.b = m_idx % P.B;
+  t.phase = m_idx / P.B;
+  t.py = t.phase >> 1; t.px = t.phase & 1;
+  t.h0 = th_i * P.BH; t.w0 = tw_i * P.BW;
+  return t;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                                 const __grid_constant__ CUtensorMap map_b,
+                                                                 const __grid_constant__ TcParams P, int tiles_m,
+                                                                 int num_tiles) {
+  using Cfg = TcCfgP<BN>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  float* s_epi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::EPI_FLOATS);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + STAGES;
+  uint64_t* tfull_bar = bars + 2 * STAGES;       // [2] accumulator ready
+  uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] accumulator drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KI = P.ntaps * P.kchunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&map_a);
+      tma_prefetch_desc(&map_b);
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "n"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(P, tile, tiles_m, BN);
+        for (int tap = 0; tap < P.ntaps; ++tap) {
+          const int dh = P.taps[tap].dh + (P.nphases == 4 ? t.py : 0);
+          const int dw = P.taps[tap].dw + (P.nphases == 4 ? t.px : 0);
+          const int plane = P.taps[tap].plane;
+          for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
+            const int s = it % STAGES;
+            if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
+            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
+            tma_load_5d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, t.w0 + dw, t.h0 + dh, t.b, plane);
+            tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0, t.phase * P.ntaps + tap);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(128, BN);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        if (lt >= 2) mbar_wait(&tempty_bar[acc], ((lt >> 1) - 1) & 1);  // epilogue drained this buffer
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+        for (int ki = 0; ki < KI; ++ki, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+          const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tfull_bar[acc]);
+      }
+    }
+  } else {
+    // ================= epilogue (warps 2..5) =================
+    const int et = threadIdx.x - 64;  // 0..127
+    const int quad = warp & 3;
+    const int m = quad * 32 + lane;
+    const int trow = P.t_ptr ? *P.t_ptr : 0;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord t = decode_tile(P, tile, tiles_m, BN);
+      const int acc = lt & 1;
+      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's reads of s_epi are done
+      {
+        const float* ssrow = P.ss ? P.ss + (long long)(trow + t.b * P.ss_img_stride) * P.ss_S + P.ss_off : nullptr;
+        for (int j = et; j < BN; j += 128) {
+          const int n = t.n0 + j;
+          float mult = 1.f, add = 0.f, bias = 0.f;
+          if (n < P.Cout) {
+            if (ssrow) { mult = ssrow[n] + 1.0f; add = ssrow[P.Cout + n]; }
+            if (P.bias) bias = P.bias[n];
+          }
+          s_epi[j] = mult; s_epi[BN + j] = add; s_epi[2 * BN + j] = bias;
+        }
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int hh = t.h0 + (m >> P.logBW), ww = t.w0 + (m & (P.BW - 1));
+      const bool pvalid = hh < P.H && ww < P.W;
+      const long long opix = ((long long)t.b * P.Hout + (hh * P.os + t.py)) * P.Wout + (ww * P.os + t.px);
+      bf16* orow = P.out + opix * P.out_pitch + t.n0;
+      const bf16* rrow = P.res ? P.res + opix * P.res_pitch + t.n0 : nullptr;
+      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_acc + (uint32_t)c0, v);
+        if (pvalid && P.out_nchw) {
+          if (hh < P.cropH && ww < P.cropW) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = t.n0 + c0 + j;
+              if (n < P.Cout) {
+                float x = __uint_as_float(v[j]);
+                x = (x + s_epi[2 * BN + c0 + j]) * s_epi[c0 + j] + s_epi[BN + c0 + j];
+                if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
+                P.out_nchw[(((long long)t.b * P.Cout + n) * P.cropH + hh) * P.cropW + ww] = x;
+              }
+            }
+          }
+        } else if (pvalid) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int cg = c0 + g * 8;
+            if (t.n0 + cg < P.Cout) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float x = __uint_as_float(v[g * 8 + j]);
+                x = (x + s_epi[2 * BN + cg + j]) * s_epi[cg + j] + s_epi[BN + cg + j];
+                if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
+                f[j] = x;
+              }
+              if (rrow) {
+                uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  f[2 * j] += __low2float(r2[j]);
+                  f[2 * j + 1] += __high2float(r2[j]);
+                }
+              }
+              uint4 o;
+              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+              *reinterpret_cast<uint4*>(orow + cg) = o;
+            }
+          }
+        }
+      }
+      // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): hand the buffer back
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+int g_num_sms = 148;
+bool g_persist = true;
+
 }  // namespace
 
 struct TcConvDesc {
@@ -336,6 +562,7 @@ struct TcConvDesc {
   TcParams P;
   int BN;
   dim3 grid;
+  int tiles_m, num_tiles;
 };
 
 bool tc_init(std::string* err) {
@@ -352,6 +579,17 @@ bool tc_init(std::string* err) {
   cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256>::SMEM_BYTES);
+  {
+    int dev = 0, n = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_num_sms = n;
+    const char* e = getenv("IRSDE_TC_PERSIST");
+    g_persist = !(e && e[0] == '0');
+  }
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
     if (err) *err = std::string("cudaFuncSetAttribute failed: ") + cudaGetErrorString(le);
@@ -402,6 +640,8 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
   d->BN = BN;
   d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
+  d->tiles_m = P.tilesW * P.tilesH * B * nphases;
+  d->num_tiles = d->tiles_m * ((Cout + BN - 1) / BN);
   // A: [planes][B][H][W][C] (C contiguous, pixel pitch in_pitch)
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B, (cuuint64_t)planes};
@@ -459,6 +699,16 @@ void tc_conv_set_runtime(TcConvDesc* d, const float* ss, const int* t_ptr, int s
 }
 
 int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
+  if (g_persist) {
+    const unsigned g = (unsigned)(d->num_tiles < g_num_sms ? d->num_tiles : g_num_sms);
+    switch (d->BN) {
+      case 32: conv_tc_persist_kernel<32><<<g, 192, TcCfgP<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
+      case 64: conv_tc_persist_kernel<64><<<g, 192, TcCfgP<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
+      case 128: conv_tc_persist_kernel<128><<<g, 192, TcCfgP<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
+      default: conv_tc_persist_kernel<256><<<g, 192, TcCfgP<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
+    }
+    return 1;
+  }
   switch (d->BN) {
     case 32: conv_tc_kernel<32><<<d->grid, 192, TcCfg<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
     case 64: conv_tc_kernel<64><<<d->grid, 192, TcCfg<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
