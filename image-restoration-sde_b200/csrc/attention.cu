@@ -351,25 +351,232 @@ __global__ void __launch_bounds__(256) la_out_kernel(const T* __restrict__ qkv, 
   for (int j = 0; j < 32; j += NV) VecIO<T>::store(orow + j, o + j);
 }
 
+// ---------------------------------------------------------------------------------------------
+// bf16 perf-mode version of pass A.  Same partial-record format, but the [64 px x 256 ch] k|v tile is
+// streamed with double-buffered cp.async and the 32x32 context of every head is accumulated with
+// warp-level mma.sync (m16n8k16, bf16 x bf16 -> fp32): ctx_h += P_h^T (32 x 64px) * V_h (64px x 32).
+// Both operands are pixel-major in shared memory, so fragments come from ldmatrix.trans.
+// Warp w owns head w/2 and d-rows 16*(w%2)..+15 (4 n-tiles of 8 e's => 16 fp32 accumulators / thread).
+// ---------------------------------------------------------------------------------------------
+static const int LAM_TP = 264;  // tile row pitch (bf16): 256 + 8 pad -> conflict-free ldmatrix
+static const int LAM_PP = 136;  // P row pitch (bf16): 128 + 8 pad
+static const size_t LAM_SMEM = (size_t)2 * LA_PIX * LAM_TP * 2 + (size_t)LA_PIX * LAM_PP * 2 + (128 * 3 + 4 * 128) * 4;
+
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                               uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__ qkv, int pitch, float* __restrict__ part,
+                                                        int N, int nchunks, int nblk) {
+  extern __shared__ __align__(16) uint8_t lam_sm[];
+  bf16* tile = reinterpret_cast<bf16*>(lam_sm);                          // [2][64][LAM_TP]  (k | v)
+  bf16* Ps = tile + 2 * LA_PIX * LAM_TP;                                 // [64][LAM_PP]
+  float* m_run = reinterpret_cast<float*>(Ps + LA_PIX * LAM_PP);         // [128]
+  float* s_run = m_run + 128;
+  float* alpha_s = s_run + 128;
+  float* red = alpha_s + 128;                                            // [4][128]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, blk = blockIdx.x;
+  if (tid < 128) { m_run[tid] = -INFINITY; s_run[tid] = 0.f; }
+  const int c0 = (int)(((long long)nchunks * blk) / nblk), c1 = (int)(((long long)nchunks * (blk + 1)) / nblk);
+  const int h = warp >> 1, dbase = h * 32 + (warp & 1) * 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  auto issue_load = [&](int ch, int buf) {
+    const int n0 = ch * LA_PIX;
+    bf16* dst = tile + buf * LA_PIX * LAM_TP;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int v = tid + i * 256;      // 2048 16-byte vectors: 32 per pixel
+      const int px = v >> 5, j = v & 31;
+      bf16* d = dst + px * LAM_TP + j * 8;
+      if (n0 + px < N) {
+        const bf16* src = qkv + ((long long)b * N + n0 + px) * pitch + 128 + j * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)), "l"(src));
+      } else {
+        *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+
+  if (c0 < c1) issue_load(c0, 0);
+  const int cp2 = (tid & 63) * 2, qtr = tid >> 6;  // stats mapping: 2 channels x 16 pixels per thread
+  const float LOG2E = 1.4426950408889634f;
+  for (int ch = c0; ch < c1; ++ch) {
+    const int buf = (ch - c0) & 1;
+    const bf16* T0 = tile + buf * LA_PIX * LAM_TP;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile[buf] landed; everyone is done with tile[buf^1] and Ps of the previous chunk
+    if (ch + 1 < c1) issue_load(ch + 1, buf ^ 1);
+    const int nvalid = min(LA_PIX, N - ch * LA_PIX);
+    // ---- per-channel max over the chunk
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int px = qtr * 16 + i;
+      if (px < nvalid) {
+        __nv_bfloat162 kk = *reinterpret_cast<const __nv_bfloat162*>(T0 + px * LAM_TP + cp2);
+        mx0 = fmaxf(mx0, __low2float(kk));
+        mx1 = fmaxf(mx1, __high2float(kk));
+      }
+    }
+    red[qtr * 128 + cp2] = mx0;
+    red[qtr * 128 + cp2 + 1] = mx1;
+    __syncthreads();
+    const float mo0 = m_run[cp2], mo1 = m_run[cp2 + 1];
+    float mn0 = mo0, mn1 = mo1;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { mn0 = fmaxf(mn0, red[q * 128 + cp2]); mn1 = fmaxf(mn1, red[q * 128 + cp2 + 1]); }
+    float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int px = qtr * 16 + i;
+      __nv_bfloat162 pp = __floats2bfloat162_rn(0.f, 0.f);
+      if (px < nvalid) {
+        __nv_bfloat162 kk = *reinterpret_cast<const __nv_bfloat162*>(T0 + px * LAM_TP + cp2);
+        pp = __floats2bfloat162_rn(exp2f((__low2float(kk) - mn0) * LOG2E), exp2f((__high2float(kk) - mn1) * LOG2E));
+        ps0 += __low2float(pp);   // sum the rounded values the MMA will actually use
+        ps1 += __high2float(pp);
+      }
+      *reinterpret_cast<__nv_bfloat162*>(Ps + px * LAM_PP + cp2) = pp;
+    }
+    __syncthreads();  // all reads of red (max) done
+    red[qtr * 128 + cp2] = ps0;
+    red[qtr * 128 + cp2 + 1] = ps1;
+    __syncthreads();
+    if (qtr == 0) {
+      const float a0 = exp2f((mo0 - mn0) * LOG2E), a1 = exp2f((mo1 - mn1) * LOG2E);  // 0 on the first chunk
+      alpha_s[cp2] = a0;
+      alpha_s[cp2 + 1] = a1;
+      s_run[cp2] = s_run[cp2] * a0 + red[cp2] + red[128 + cp2] + red[256 + cp2] + red[384 + cp2];
+      s_run[cp2 + 1] = s_run[cp2 + 1] * a1 + red[cp2 + 1] + red[128 + cp2 + 1] + red[256 + cp2 + 1] + red[384 + cp2 + 1];
+      m_run[cp2] = mn0;
+      m_run[cp2 + 1] = mn1;
+    }
+    __syncthreads();
+    // ---- rescale and accumulate: rows g / g+8 of this warp's 16 d-rows
+    {
+      const float al_lo = alpha_s[dbase + (lane >> 2)], al_hi = alpha_s[dbase + (lane >> 2) + 8];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) { acc[nt][0] *= al_lo; acc[nt][1] *= al_lo; acc[nt][2] *= al_hi; acc[nt][3] *= al_hi; }
+    }
+    const uint32_t Pbase = (uint32_t)__cvta_generic_to_shared(Ps);
+    const uint32_t Vbase = (uint32_t)__cvta_generic_to_shared(T0);
+    const int mi = lane >> 3, r8 = lane & 7;  // ldmatrix: lane supplies row r8 of matrix mi
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const int k0 = ks * 16;
+      uint32_t a0, a1, a2, a3;
+      // A = P^T: matrices (k0-7,m0-7) (k0-7,m8-15) (k8-15,m0-7) (k8-15,m8-15) -> a0,a1,a2,a3 after transpose
+      ldsm_x4_trans(Pbase + (uint32_t)(((k0 + (mi >> 1) * 8 + r8) * LAM_PP + dbase + (mi & 1) * 8) * 2), a0, a1, a2, a3);
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {  // two pairs of n-tiles (16 e's each)
+        uint32_t b0, b1, b2, b3;
+        // B = V: matrices (k0-7,n0-7) (k8-15,n0-7) (k0-7,n8-15) (k8-15,n8-15)
+        ldsm_x4_trans(Vbase + (uint32_t)(((k0 + (mi & 1) * 8 + r8) * LAM_TP + 128 + h * 32 + np * 16 + (mi >> 1) * 8) * 2), b0,
+                      b1, b2, b3);
+        mma_bf16_16816(acc[np * 2], a0, a1, a2, a3, b0, b1);
+        mma_bf16_16816(acc[np * 2 + 1], a0, a1, a2, a3, b2, b3);
+      }
+    }
+  }
+  __syncthreads();
+  float* rec = part + ((long long)b * LA_MAXBLK + blk) * LA_REC;
+  if (tid < 128) {
+    const int hh = tid >> 5, dd = tid & 31;
+    rec[hh * 1088 + dd] = m_run[tid];
+    rec[hh * 1088 + 32 + dd] = s_run[tid];
+  }
+  {
+    const int g = lane >> 2, t4 = lane & 3, drow = (warp & 1) * 16 + g;
+    float* cp = rec + h * 1088 + 64;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const int e = nt * 8 + t4 * 2;
+      *reinterpret_cast<float2*>(cp + drow * 32 + e) = make_float2(acc[nt][0], acc[nt][1]);
+      *reinterpret_cast<float2*>(cp + (drow + 8) * 32 + e) = make_float2(acc[nt][2], acc[nt][3]);
+    }
+  }
+}
+
 static bool g_la_attr_done = false;
 
 template <typename T>
-void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
-                    cudaStream_t st) {
+static void launch_la_kv(const T* qkv, int qkv_pitch, float* partial, int B, int N, int nchunks, int nblk, size_t smem,
+                         cudaStream_t st);
+template <>
+void launch_la_kv<float>(const float* qkv, int qkv_pitch, float* partial, int B, int N, int nchunks, int nblk, size_t smem,
+                         cudaStream_t st) {
+  la_kv_kernel<float><<<dim3(nblk, B), 256, smem, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+}
+template <>
+void launch_la_kv<bf16>(const bf16* qkv, int qkv_pitch, float* partial, int B, int N, int nchunks, int nblk, size_t smem,
+                        cudaStream_t st) {
+  if (qkv_pitch % 8 == 0 && ((uintptr_t)qkv % 16) == 0)
+    la_kv_mma_kernel<<<dim3(nblk, B), 256, LAM_SMEM, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+  else
+    la_kv_kernel<bf16><<<dim3(nblk, B), 256, smem, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+}
+
+template <typename T>
+void launch_linattn_ctx(const T* qkv, int qkv_pitch, float* partial, float* ctx, int B, int N, cudaStream_t st) {
   const int nchunks = (N + LA_PIX - 1) / LA_PIX;
   const int nblk = la_blocks_per_image(B, N);
   const size_t smem = (size_t)(2 * LA_PIX * 128 + 128 * 5) * sizeof(float);
   if (!g_la_attr_done) {
     cudaFuncSetAttribute(la_kv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(la_kv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(la_kv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAM_SMEM);
     g_la_attr_done = true;
   }
-  la_kv_kernel<T><<<dim3(nblk, B), 256, smem, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+  launch_la_kv<T>(qkv, qkv_pitch, partial, B, N, nchunks, nblk, smem, st);
   la_combine_kernel<<<B * 4, 1024, 0, st>>>(partial, ctx, N, nblk);
+}
+template void launch_linattn_ctx<float>(const float*, int, float*, float*, int, int, cudaStream_t);
+template void launch_linattn_ctx<bf16>(const bf16*, int, float*, float*, int, int, cudaStream_t);
+
+template <typename T>
+void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
+                    cudaStream_t st) {
+  launch_linattn_ctx<T>(qkv, qkv_pitch, partial, ctx, B, N, st);
   la_out_kernel<T><<<dim3((N + 63) / 64, B), 256, 0, st>>>(qkv, qkv_pitch, ctx, hidden, hid_pitch, N);
 }
 template void launch_linattn<float>(const float*, int, float*, float*, float*, int, int, int, cudaStream_t);
 template void launch_linattn<bf16>(const bf16*, int, float*, float*, bf16*, int, int, int, cudaStream_t);
+
+// Fold the per-image context into the to_out 1x1 weights so that pass C and the to_out conv become ONE
+// per-image-weight GEMM on the (head-softmaxed) q:  y[px][c] = sum_k qs[px][k] * Mb[b][c][k],
+// Mb[b][c][h*32+d] = sum_e Wout[c][h*32+e] * ctx[b][h][d][e]   (module_util.py:176-178 re-associated).
+__global__ void la_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wout, bf16* __restrict__ Mb, int C) {
+  __shared__ float cs[4][32][33];
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 4096; i += blockDim.x) cs[i >> 10][(i >> 5) & 31][i & 31] = ctx[(long long)b * 4096 + i];
+  __syncthreads();
+  const int c = blockIdx.x * 2 + (threadIdx.x >> 7), k = threadIdx.x & 127;
+  if (c >= C) return;
+  const int h = k >> 5, d = k & 31;
+  const float* w = wout + (long long)c * 128 + h * 32;
+  float acc = 0.f;
+#pragma unroll
+  for (int e = 0; e < 32; ++e) acc += w[e] * cs[h][d][e];
+  Mb[((long long)b * C + c) * 128 + k] = __float2bfloat16_rn(acc);
+}
+void launch_la_fold(const float* ctx, const float* wout, bf16* Mb, int B, int C, cudaStream_t st) {
+  la_fold_kernel<<<dim3((C + 1) / 2, B), 256, 0, st>>>(ctx, wout, Mb, C);
+}
 
 // =============================================================================================
 // full softmax attention (module_util.py:192-204) - denoising-sde mid_attn only.

@@ -78,6 +78,11 @@ template <typename T>
 void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
                     cudaStream_t st);
 size_t linattn_partial_floats(int B, int N);
+// passes A+B only (k,v -> ctx); and the fold of ctx into the to_out weights:
+//   Mb[b][c][h*32+d] = sum_e Wout[c][h*32+e] * ctx[b][h][d][e]   (bf16, K-major rows of 128)
+template <typename T>
+void launch_linattn_ctx(const T* qkv, int qkv_pitch, float* partial, float* ctx, int B, int N, cudaStream_t st);
+void launch_la_fold(const float* ctx, const float* wout, bf16* Mb, int B, int C, cudaStream_t st);
 // full softmax attention (denoising-sde mid_attn): qkv [B,N,384] -> hidden [B,N,128]
 template <typename T>
 void launch_fullattn(const T* qkv, int qkv_pitch, T* hidden, int hid_pitch, int B, int N, cudaStream_t st);
@@ -111,7 +116,9 @@ struct TcConvDesc;  // opaque: tensor maps + tap table + tile config
 TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win, int Cin, int planes,
                            const bf16* wpacked /*[phase][tap][Cout][Cin]*/, int Cout, int ntaps, const TcTap* taps,
                            int nphases /*1 or 4 (upsample phases)*/, const Epilogue& ep, bf16* out, int out_pitch,
-                           int Hout, int Wout, std::string* err);
+                           int Hout, int Wout, std::string* err, int flags = 0);
+enum { TC_FLAG_QSOFTMAX = 1, TC_FLAG_W_PER_IMAGE = 2 };
+bool tc_fused_attention_available();
 void tc_conv_destroy(TcConvDesc*);
 void tc_conv_set_runtime(TcConvDesc*, const float* ss, const int* t_ptr, int ss_img_stride);
 void tc_conv_set_out_nchw(TcConvDesc*, float* out, int cropH, int cropW);  // out==nullptr at create => fp32 NCHW output

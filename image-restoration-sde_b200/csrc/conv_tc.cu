@@ -43,6 +43,9 @@ struct TcParams {
   int out_pitch;
   float* out_nchw;      // if set: write fp32 NCHW cropped to (cropH, cropW) instead of the NHWC view
   int cropH, cropW;
+  int tma_store;        // persistent kernel: bf16 NHWC output through smem + TMA bulk store
+  int qsm;              // LinearAttention q: softmax over each 32-channel head * 32^-0.5 for output channels < 128
+  int w_per_image;      // weights tensor is [B][Cout][Cin]: third TMA coordinate = image index
   const bf16* res;
   int res_pitch;
   const float* bias;
@@ -342,13 +345,26 @@ struct TcCfgP {
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_FLOATS = 3 * BN;
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 256;
+  static constexpr int STG_BYTES = 4 * 2 * 2048;  // per epilogue warp: 2 x (32 rows x 64 B) staging for TMA stores
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 256;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+
+struct OutMaps {
+  CUtensorMap m[4];  // one per upsample phase (only m[0] otherwise)
+};
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void* smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(map),
+               "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct TileCoord {
   int b, phase, py, px, h0, w0, n0;
@@ -369,6 +385,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
 template <int BN>
 __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b,
+                                                                 const __grid_constant__ OutMaps map_o,
                                                                  const __grid_constant__ TcParams P, int tiles_m,
                                                                  int num_tiles) {
   using Cfg = TcCfgP<BN>;
@@ -377,7 +394,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  float* s_epi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint8_t* smem_stg = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stages are multiples of 1024)
+  float* s_epi = reinterpret_cast<float*>(smem_stg + Cfg::STG_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::EPI_FLOATS);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
@@ -430,7 +448,8 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
             if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
             mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
             tma_load_5d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, t.w0 + dw, t.h0 + dh, t.b, plane);
-            tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0, t.phase * P.ntaps + tap);
+            tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0,
+                        t.phase * P.ntaps + tap + (P.w_per_image ? t.b : 0));
           }
         }
       }
@@ -466,6 +485,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     const int m = quad * 32 + lane;
     const int trow = P.t_ptr ? *P.t_ptr : 0;
     int lt = 0;
+    uint32_t nstore = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const TileCoord t = decode_tile(P, tile, tiles_m, BN);
       const int acc = lt & 1;
@@ -508,6 +528,64 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
               }
             }
           }
+        } else if (P.tma_store) {
+          // bf16 NHWC through shared memory + TMA store: each lane owns one pixel row of 32 channels (64 B);
+          // the staging tile uses the 64B swizzle so the 16-byte st.shared are conflict free and the bulk
+          // store writes full, coalesced lines (out-of-range pixels / channels are clipped by TMA).
+          if (P.qsm && t.n0 + c0 < 128) {  // one chunk == one attention head of this pixel's q (module_util.py:168,171)
+            float mx = __uint_as_float(v[0]);
+#pragma unroll
+            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+            float sm = 0.f;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float e = __expf(__uint_as_float(v[j]) - mx);
+              v[j] = __float_as_uint(e);
+              sm += e;
+            }
+            const float inv = __fdividef(0.17677669529663687f, sm);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * inv);
+          }
+          uint4 ov[4];
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            const int cg = c0 + g * 8;
+            float f[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float x = __uint_as_float(v[g * 8 + j]);
+              x = (x + s_epi[2 * BN + cg + j]) * s_epi[cg + j] + s_epi[BN + cg + j];
+              if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
+              f[j] = x;
+            }
+            if (rrow && pvalid && t.n0 + cg < P.Cout) {
+              uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                f[2 * j] += __low2float(r2[j]);
+                f[2 * j + 1] += __high2float(r2[j]);
+              }
+            }
+            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov[g]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+          }
+          uint8_t* stg = smem_stg + (warp - 2) * 4096 + (nstore & 1) * 2048;
+          if (lane == 0) bulk_wait_read1();  // the store issued two chunks ago has finished reading this buffer
+          __syncwarp();
+#pragma unroll
+          for (int g = 0; g < 4; ++g)
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((g ^ ((lane >> 1) & 3)) << 4)) = ov[g];
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            const int m0 = quad * 32;
+            tma_store_4d(&map_o.m[t.phase], stg, t.n0 + c0, t.w0 + (m0 & (P.BW - 1)), t.h0 + (m0 >> P.logBW), t.b);
+            bulk_commit();
+          }
+          ++nstore;
         } else if (pvalid) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
@@ -544,6 +622,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (lane == 0) bulk_wait_all();  // staging smem must stay valid until the last bulk store has read it
   }
   tc_fence_before();
   __syncthreads();
@@ -554,11 +633,13 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
 
 int g_num_sms = 148;
 bool g_persist = true;
+bool g_tma_store = true;
 
 }  // namespace
 
 struct TcConvDesc {
   CUtensorMap map_a, map_b;
+  OutMaps map_o;
   TcParams P;
   int BN;
   dim3 grid;
@@ -589,6 +670,8 @@ bool tc_init(std::string* err) {
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_num_sms = n;
     const char* e = getenv("IRSDE_TC_PERSIST");
     g_persist = !(e && e[0] == '0');
+    e = getenv("IRSDE_TC_TMA_STORE");
+    g_tma_store = !(e && e[0] == '0');
   }
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
@@ -601,7 +684,7 @@ bool tc_init(std::string* err) {
 
 TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win, int Cin, int planes,
                            const bf16* wpacked, int Cout, int ntaps, const TcTap* taps, int nphases, const Epilogue& ep,
-                           bf16* out, int out_pitch, int Hout, int Wout, std::string* err) {
+                           bf16* out, int out_pitch, int Hout, int Wout, std::string* err, int flags) {
   auto bad = [&](const char* m) -> TcConvDesc* {
     if (err) *err = m;
     return nullptr;
@@ -626,6 +709,10 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   P.bias = ep.bias; P.ss = ep.ss; P.t_ptr = ep.t_ptr; P.ss_S = ep.ss_S; P.ss_off = ep.ss_off;
   P.ss_img_stride = ep.ss_img_stride; P.silu = ep.silu;
   for (int i = 0; i < ntaps; ++i) P.taps[i] = taps[i];
+  P.qsm = (flags & TC_FLAG_QSOFTMAX) ? 1 : 0;
+  P.w_per_image = (flags & TC_FLAG_W_PER_IMAGE) ? 1 : 0;
+  if (P.w_per_image && (ntaps != 1 || nphases != 1)) return bad("per-image weights need a 1x1 conv");
+  if ((P.qsm || P.w_per_image) && !(g_persist && g_tma_store)) return bad("fused attention epilogues need the persistent TMA-store kernel");
   // tile shape: BW x BH = 128 pixels, minimise padded work
   long long best = -1;
   for (int bw = 128; bw >= 8; bw >>= 1) {
@@ -668,7 +755,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   }
   // B: [phase*ntaps][Cout][Cin]
   {
-    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout_w, (cuuint64_t)(nphases * ntaps)};
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout_w, (cuuint64_t)(P.w_per_image ? B : nphases * ntaps)};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout_w * Cin * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
     cuuint32_t es[3] = {1, 1, 1};
@@ -681,10 +768,34 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
       return nullptr;
     }
   }
+  // output maps for the TMA-store epilogue: [B][H][W][C] view of the destination (channel offset already in
+  // `out`), pixel stride os*pitch; one map per upsample phase (base shifted by (py,px))
+  memset(&d->map_o, 0, sizeof d->map_o);
+  P.tma_store = 0;
+  if (!nchw_out && g_tma_store) {
+    const int bw = P.BW < 32 ? P.BW : 32, bh = 32 / bw;
+    bool ok = true;
+    for (int ph = 0; ph < nphases && ok; ++ph) {
+      const int py = ph >> 1, px = ph & 1;
+      bf16* base = out + ((long long)py * Wout + px) * out_pitch;
+      cuuint64_t dims[4] = {(cuuint64_t)Cout, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B};
+      cuuint64_t strides[3] = {(cuuint64_t)P.os * out_pitch * 2, (cuuint64_t)P.os * Wout * out_pitch * 2,
+                               (cuuint64_t)Hout * Wout * out_pitch * 2};
+      cuuint32_t box[4] = {32, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+      cuuint32_t es[4] = {1, 1, 1, 1};
+      CUresult r = g_encode(&d->map_o.m[ph], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, es,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      ok = (r == CUDA_SUCCESS);
+    }
+    P.tma_store = ok ? 1 : 0;
+  }
   return d;
 }
 
 void tc_conv_destroy(TcConvDesc* d) { delete d; }
+
+bool tc_fused_attention_available() { return g_persist && g_tma_store; }
 
 void tc_conv_set_out_nchw(TcConvDesc* d, float* out, int cropH, int cropW) {
   d->P.out_nchw = out;
@@ -702,10 +813,10 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
   if (g_persist) {
     const unsigned g = (unsigned)(d->num_tiles < g_num_sms ? d->num_tiles : g_num_sms);
     switch (d->BN) {
-      case 32: conv_tc_persist_kernel<32><<<g, 192, TcCfgP<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
-      case 64: conv_tc_persist_kernel<64><<<g, 192, TcCfgP<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
-      case 128: conv_tc_persist_kernel<128><<<g, 192, TcCfgP<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
-      default: conv_tc_persist_kernel<256><<<g, 192, TcCfgP<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P, d->tiles_m, d->num_tiles); break;
+      case 32: conv_tc_persist_kernel<32><<<g, 192, TcCfgP<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+      case 64: conv_tc_persist_kernel<64><<<g, 192, TcCfgP<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+      case 128: conv_tc_persist_kernel<128><<<g, 192, TcCfgP<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+      default: conv_tc_persist_kernel<256><<<g, 192, TcCfgP<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
     }
     return 1;
   }

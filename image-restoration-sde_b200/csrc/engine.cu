@@ -7,6 +7,7 @@
 // pixel row is one 128-byte line (the TMA / UMMA swizzle atom of the tensor-core engine).
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -46,6 +47,8 @@ struct OpRec {
   int cat;
   double flops;  // executed multiply-add flops (2*MAC) of this op, 0 for memory-bound ops
   Op fn;
+  std::string label;   // for IRSDE_PROFILE_DUMP
+  double bytes = 0.0;  // algorithmic HBM bytes (inputs + outputs + weights once)
 };
 
 struct Plan {
@@ -88,7 +91,7 @@ struct irsde_ctx {
   std::vector<void*> allocs;
   bool tc_ok = false;
   bool prof = false;
-  struct ProfEv { int cat; double flops; cudaEvent_t e0, e1; };
+  struct ProfEv { int cat; double flops; cudaEvent_t e0, e1; const OpRec* op; };
   std::vector<ProfEv> prof_events;
   bool use_tc = false;  // bf16 mode: route eligible convs through the tcgen05 engine
 };
@@ -323,7 +326,24 @@ struct Builder {
 
   // generic conv op. ss_block = ResBlock prefix whose (scale,shift) modulate the output ("" = none)
   void conv(const std::string& wname, V in, int Hin, int Win, int K, int stride, int pad, int up, const char* bias,
-            const std::string& ss_block, int silu, const V* res, V out, int Cout, float** out_nchw_slot = nullptr) {
+            const std::string& ss_block, int silu, const V* res, V out, int Cout, float** out_nchw_slot = nullptr,
+            int tc_flags = 0, const bf16* w_override = nullptr) {
+    size_t first = plan->ops.size();
+    conv_impl(wname, in, Hin, Win, K, stride, pad, up, bias, ss_block, silu, res, out, Cout, out_nchw_slot, tc_flags, w_override);
+    if (plan->ops.size() > first) {
+      OpRec& r = plan->ops.back();
+      char b[160];
+      int Ho = (Hin * up + 2 * pad - K) / stride + 1, Wo = (Win * up + 2 * pad - K) / stride + 1;
+      snprintf(b, sizeof b, "%s %dx%d k%d s%d up%d Cin%d Cout%d", wname.c_str(), Hin, Win, K, stride, up, in.C, Cout);
+      r.label = b;
+      double esz = sizeof(T);
+      r.bytes = (double)plan->B * Hin * Win * in.C * esz + (double)plan->B * Ho * Wo * Cout * (out_nchw_slot ? 4.0 : esz) +
+                (double)K * K * in.C * Cout * esz + (res ? (double)plan->B * Ho * Wo * Cout * esz : 0.0);
+    }
+  }
+  void conv_impl(const std::string& wname, V in, int Hin, int Win, int K, int stride, int pad, int up, const char* bias,
+                 const std::string& ss_block, int silu, const V* res, V out, int Cout, float** out_nchw_slot, int tc_flags,
+                 const bf16* w_override) {
     ConvGeom g;
     g.B = plan->B; g.Hin = Hin; g.Win = Win; g.Cin = in.C; g.up = up; g.KH = K; g.KW = K; g.stride = stride; g.pad = pad;
     g.Hout = (Hin * up + 2 * pad - K) / stride + 1;
@@ -365,7 +385,7 @@ struct Builder {
       }
       if (ctx->use_tc && shape_ok && in.C % 8 == 0 && in.pitch % 8 == 0 &&
           (nchw ? (K == 3 && up == 1) : (Cout % 8 == 0 && out.pitch % 8 == 0))) {
-        const bf16* wt = ctx->w_tc[wname];
+        const bf16* wt = w_override ? w_override : ctx->w_tc[wname];
         if (!wt) { ok = false; err = "unpacked tc weight " + wname; return; }
         TcTap taps[16];
         int ntaps = 0, nph = 1, planes = 1, Ha = Hin, Wa = Win, a_pitch = in.pitch;
@@ -392,7 +412,7 @@ struct Builder {
         }
         std::string terr;
         TcConvDesc* d = tc_conv_create(a_ptr, a_pitch, plan->B, Ha, Wa, in.C, planes, wt, Cout, ntaps, taps, nph, ep, out.p,
-                                       out.pitch, g.Hout, g.Wout, &terr);
+                                       out.pitch, g.Hout, g.Wout, &terr, tc_flags);
         if (!d) { ok = false; err = "tc_conv_create(" + wname + "): " + terr; return; }
         plan->tc_descs.push_back(d);
         int cH = plan->H, cW = plan->W;
@@ -405,6 +425,7 @@ struct Builder {
         return;
       }
     }
+    if (tc_flags || w_override) { ok = false; err = "fused attention conv needs the tensor-core engine: " + wname; return; }
     const float* w = ctx->w_simt[wname];
     if (!w) { ok = false; err = "unpacked weight " + wname; return; }
     int H = plan->H, Wd = plan->W;
@@ -444,7 +465,47 @@ struct Builder {
       launch_layernorm<T>(in.p, in.pitch, g1, nullptr, 0, xn, C, npix, C, st);
       c->launches++;
     }});
+    plan->ops.back().label = pre + "norm";
+    plan->ops.back().bytes = 2.0 * npix * C * sizeof(T);
     T* qkv = tmp(npix * 384);
+    if constexpr (std::is_same<T, bf16>::value) {
+      if (!full && ctx->use_tc && tc_fused_attention_available() && C % 8 == 0) {
+        // Fused LinearAttention: (1) the to_qkv GEMM epilogue applies softmax_d(q)*32^-.5 per head, (2) k,v -> ctx,
+        // (3) ctx is folded into the to_out weights per image, (4) ONE per-image-weight 1x1 GEMM on q gives to_out's
+        // output (module_util.py:163-178 with the two einsums + to_out conv re-associated), (5) LayerNorm + residual.
+        conv(pre + "fn.fn.to_qkv.weight", V{xn, C, C}, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384, nullptr,
+             TC_FLAG_QSOFTMAX);
+        release(xn);
+        plan->ops.push_back(OpRec{CAT_ATTN, 0.0, [=](Plan*, cudaStream_t st) {
+          launch_linattn_ctx<T>(qkv, 384, la_partial, la_ctx, B, N, st);
+          c->launches += 2;
+        }});
+        plan->ops.back().label = pre + "linattn kv->ctx (2 kernels)";
+        plan->ops.back().bytes = (double)npix * 256 * sizeof(T);
+        bf16* Mb = tmp((long long)B * C * 128);
+        float* wout = fw(pre + "fn.fn.to_out.0.weight");
+        plan->ops.push_back(OpRec{CAT_ATTN, 0.0, [=](Plan*, cudaStream_t st) {
+          launch_la_fold(la_ctx, wout, Mb, B, C, st);
+          c->launches++;
+        }});
+        plan->ops.back().label = pre + "fold ctx into to_out";
+        T* y = tmp(npix * C);
+        std::string bn = pre + "fn.fn.to_out.0.bias";
+        conv(pre + "fn.fn.to_out.0.weight", V{qkv, 384, 128}, H, W, 1, 1, 0, 1, bn.c_str(), "", 0, nullptr, V{y, C, C}, C, nullptr,
+             TC_FLAG_W_PER_IMAGE, Mb);
+        float* g2 = fw(pre + "fn.fn.to_out.1.g");
+        plan->ops.push_back(OpRec{CAT_LN, 0.0, [=](Plan*, cudaStream_t st) {
+          launch_layernorm<T>(y, C, g2, in.p, in.pitch, out.p, out.pitch, npix, C, st);
+          c->launches++;
+        }});
+        plan->ops.back().label = pre + "to_out.norm+res";
+        plan->ops.back().bytes = 3.0 * npix * C * sizeof(T);
+        release(y);
+        release(Mb);
+        release(qkv);
+        return;
+      }
+    }
     conv(pre + "fn.fn.to_qkv.weight", V{xn, C, C}, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384);
     release(xn);
     T* hid = tmp(npix * 128);
@@ -460,6 +521,8 @@ struct Builder {
         launch_linattn<T>(qkv, 384, la_partial, la_ctx, hid, 128, B, N, st);
         c->launches += 3;
       }});
+      plan->ops.back().label = pre + "linattn(3 kernels)";
+      plan->ops.back().bytes = (double)npix * (384 + 128) * sizeof(T);
       T* y = tmp(npix * C);
       std::string bn = pre + "fn.fn.to_out.0.bias";
       conv(pre + "fn.fn.to_out.0.weight", V{hid, 128, 128}, H, W, 1, 1, 0, 1, bn.c_str(), "", 0, nullptr, V{y, C, C}, C);
@@ -468,6 +531,8 @@ struct Builder {
         launch_layernorm<T>(y, C, g2, in.p, in.pitch, out.p, out.pitch, npix, C, st);
         c->launches++;
       }});
+      plan->ops.back().label = pre + "to_out.norm+res";
+      plan->ops.back().bytes = 3.0 * npix * C * sizeof(T);
       release(y);
     }
     release(qkv);
@@ -628,7 +693,7 @@ void run_forward(irsde_ctx* ctx, Plan* p, cudaStream_t st) {
     cudaEventRecord(e0, st);
     op.fn(p, st);
     cudaEventRecord(e1, st);
-    ctx->prof_events.push_back({op.cat, op.flops, e0, e1});
+    ctx->prof_events.push_back({op.cat, op.flops, e0, e1, &op});
   }
 }
 
@@ -998,9 +1063,13 @@ int irsde_profile_end(irsde_ctx* ctx, double* ms, double* flops, int64_t* launch
   ctx->prof = false;
   CUDA_TRY(ctx, cudaDeviceSynchronize());
   for (int i = 0; i < ncat; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  const char* dump = getenv("IRSDE_PROFILE_DUMP");
   for (auto& e : ctx->prof_events) {
     float t = 0.f;
     cudaEventElapsedTime(&t, e.e0, e.e1);
+    if (dump && dump[0] == '1' && e.op)
+      fprintf(stderr, "PROF\t%d\t%.4f\t%.1f\t%.1f\t%s\n", e.cat, t, e.op->flops > 0 ? e.op->flops / (t * 1e-3) / 1e12 : 0.0,
+              e.op->bytes > 0 ? e.op->bytes / (t * 1e-3) / 1e9 : 0.0, e.op->label.c_str());
     ms[e.cat] += t;
     flops[e.cat] += e.flops;
     launches[e.cat] += 1;
