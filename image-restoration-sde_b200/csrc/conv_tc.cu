@@ -151,6 +151,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_async(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
+// The registers are tied to the wait ("+r") so the compiler cannot schedule their consumers above it.
+__device__ __forceinline__ void tmem_ld_wait(uint32_t v[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
 constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16
 
 template <int BN>
@@ -345,7 +367,7 @@ struct TcCfgP {
   static constexpr int B_STAGE_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
   static constexpr int EPI_FLOATS = 3 * BN;
-  static constexpr int STG_BYTES = 4 * 2 * 2048;  // per epilogue warp: 2 x (32 rows x 64 B) staging for TMA stores
+  static constexpr int STG_BYTES = 8 * 2048;  // per epilogue warp: one 32 rows x 64 B staging tile for TMA stores
   static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 256;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
@@ -363,7 +385,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
                : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct TileCoord {
@@ -383,7 +405,7 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
 }
 
 template <int BN>
-__global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
+__global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                  const __grid_constant__ OutMaps map_o,
                                                                  const __grid_constant__ TcParams P, int tiles_m,
@@ -413,7 +435,7 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -479,101 +501,102 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
       }
     }
   } else {
-    // ================= epilogue (warps 2..5) =================
-    const int et = threadIdx.x - 64;  // 0..127
+    // ================= epilogue (warps 2..9) =================
+    // Two warps per TMEM lane quadrant (warp & 3), taking alternate 32-column chunks; the tcgen05.ld of the next
+    // chunk is in flight while the current one is converted, staged (64B-swizzled) and bulk-stored by TMA.
+    const int et = threadIdx.x - 64;  // 0..255
     const int quad = warp & 3;
+    const int half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int trow = P.t_ptr ? *P.t_ptr : 0;
+    const bool affine = (P.ss != nullptr) || (P.bias != nullptr);
+    uint8_t* stg = smem_stg + (warp - 2) * 2048;
     int lt = 0;
-    uint32_t nstore = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const TileCoord t = decode_tile(P, tile, tiles_m, BN);
       const int acc = lt & 1;
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // previous tile's reads of s_epi are done
-      {
+      if (affine) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's reads of s_epi are done
         const float* ssrow = P.ss ? P.ss + (long long)(trow + t.b * P.ss_img_stride) * P.ss_S + P.ss_off : nullptr;
-        for (int j = et; j < BN; j += 128) {
+        for (int j = et; j < BN; j += 256) {
           const int n = t.n0 + j;
           float mult = 1.f, add = 0.f, bias = 0.f;
           if (n < P.Cout) {
             if (ssrow) { mult = ssrow[n] + 1.0f; add = ssrow[P.Cout + n]; }
             if (P.bias) bias = P.bias[n];
           }
-          s_epi[j] = mult; s_epi[BN + j] = add; s_epi[2 * BN + j] = bias;
+          s_epi[j] = mult; s_epi[BN + j] = bias * mult + add;  // (x + bias) * mult + add == x * mult + (bias * mult + add)
         }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int hh = t.h0 + (m >> P.logBW), ww = t.w0 + (m & (P.BW - 1));
       const bool pvalid = hh < P.H && ww < P.W;
       const long long opix = ((long long)t.b * P.Hout + (hh * P.os + t.py)) * P.Wout + (ww * P.os + t.px);
       bf16* orow = P.out + opix * P.out_pitch + t.n0;
       const bf16* rrow = P.res ? P.res + opix * P.res_pitch + t.n0 : nullptr;
-      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
-      tc_fence_after();
-      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_acc + (uint32_t)c0, v);
-        if (pvalid && P.out_nchw) {
-          if (hh < P.cropH && ww < P.cropW) {
+
+      auto process = [&](uint32_t* v, const int c0) {
+        if (P.qsm && t.n0 + c0 < 128) {  // one chunk == one attention head of this pixel's q (module_util.py:168,171)
+          float mx = __uint_as_float(v[0]);
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+          float sm = 0.f;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float e = __expf(__uint_as_float(v[j]) - mx);
+            v[j] = __float_as_uint(e);
+            sm += e;
+          }
+          const float inv = __fdividef(0.17677669529663687f, sm);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * inv);
+        }
+        if (affine) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), s_epi[c0 + j], s_epi[BN + c0 + j]));
+        }
+        if (P.silu) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = __uint_as_float(v[j]);
+            v[j] = __float_as_uint(__fdividef(x, 1.0f + __expf(-x)));
+          }
+        }
+        if (P.out_nchw) {
+          if (pvalid && hh < P.cropH && ww < P.cropW) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = t.n0 + c0 + j;
-              if (n < P.Cout) {
-                float x = __uint_as_float(v[j]);
-                x = (x + s_epi[2 * BN + c0 + j]) * s_epi[c0 + j] + s_epi[BN + c0 + j];
-                if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
-                P.out_nchw[(((long long)t.b * P.Cout + n) * P.cropH + hh) * P.cropW + ww] = x;
-              }
+              if (n < P.Cout) P.out_nchw[(((long long)t.b * P.Cout + n) * P.cropH + hh) * P.cropW + ww] = __uint_as_float(v[j]);
             }
           }
-        } else if (P.tma_store) {
-          // bf16 NHWC through shared memory + TMA store: each lane owns one pixel row of 32 channels (64 B);
-          // the staging tile uses the 64B swizzle so the 16-byte st.shared are conflict free and the bulk
-          // store writes full, coalesced lines (out-of-range pixels / channels are clipped by TMA).
-          if (P.qsm && t.n0 + c0 < 128) {  // one chunk == one attention head of this pixel's q (module_util.py:168,171)
-            float mx = __uint_as_float(v[0]);
+          return;
+        }
+        uint4 ov[4];
 #pragma unroll
-            for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-            float sm = 0.f;
+        for (int g = 0; g < 4; ++g) {
+          const int cg = c0 + g * 8;
+          float f[8];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float e = __expf(__uint_as_float(v[j]) - mx);
-              v[j] = __float_as_uint(e);
-              sm += e;
+          for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
+          if (rrow && pvalid && t.n0 + cg < P.Cout) {
+            uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
+            const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              f[2 * j] += __low2float(r2[j]);
+              f[2 * j + 1] += __high2float(r2[j]);
             }
-            const float inv = __fdividef(0.17677669529663687f, sm);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * inv);
           }
-          uint4 ov[4];
+          __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov[g]);
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cg = c0 + g * 8;
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(v[g * 8 + j]);
-              x = (x + s_epi[2 * BN + cg + j]) * s_epi[cg + j] + s_epi[BN + cg + j];
-              if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
-              f[j] = x;
-            }
-            if (rrow && pvalid && t.n0 + cg < P.Cout) {
-              uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[2 * j] += __low2float(r2[j]);
-                f[2 * j + 1] += __high2float(r2[j]);
-              }
-            }
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&ov[g]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-          }
-          uint8_t* stg = smem_stg + (warp - 2) * 4096 + (nstore & 1) * 2048;
-          if (lane == 0) bulk_wait_read1();  // the store issued two chunks ago has finished reading this buffer
+          for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+        }
+        if (P.tma_store) {
+          // bf16 NHWC through shared memory + TMA store: each lane owns one pixel row of 32 channels (64 B); the
+          // staging tile uses the 64B swizzle so the 16-byte st.shared are conflict free and the bulk store writes
+          // full, coalesced lines (out-of-range pixels / channels are clipped by TMA).
+          if (lane == 0) bulk_wait_read0();  // the previous bulk store has finished reading the staging tile
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g)
@@ -585,39 +608,30 @@ __global__ void __launch_bounds__(192, 1) conv_tc_persist_kernel(const __grid_co
             tma_store_4d(&map_o.m[t.phase], stg, t.n0 + c0, t.w0 + (m0 & (P.BW - 1)), t.h0 + (m0 >> P.logBW), t.b);
             bulk_commit();
           }
-          ++nstore;
         } else if (pvalid) {
 #pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            const int cg = c0 + g * 8;
-            if (t.n0 + cg < P.Cout) {
-              float f[8];
+          for (int g = 0; g < 4; ++g)
+            if (t.n0 + c0 + g * 8 < P.Cout) *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov[g];
+        }
+      };
+
+      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
+      tc_fence_after();
+      const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
+      constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp
+      uint32_t v[2][32];
+      if (half * 32 < BN) tmem_ld32_async(tmem_acc + (uint32_t)(half * 32), v[0]);
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
-                float x = __uint_as_float(v[g * 8 + j]);
-                x = (x + s_epi[2 * BN + cg + j]) * s_epi[cg + j] + s_epi[BN + cg + j];
-                if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
-                f[j] = x;
-              }
-              if (rrow) {
-                uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  f[2 * j] += __low2float(r2[j]);
-                  f[2 * j + 1] += __high2float(r2[j]);
-                }
-              }
-              uint4 o;
-              __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-              *reinterpret_cast<uint4*>(orow + cg) = o;
-            }
-          }
+      for (int i = 0; i < NCH; ++i) {
+        const int c0 = (2 * i + half) * 32;
+        if (c0 < BN) {
+          tmem_ld_wait(v[i & 1]);
+          const int c1 = (2 * (i + 1) + half) * 32;
+          if (i + 1 < NCH && c1 < BN) tmem_ld32_async(tmem_acc + (uint32_t)c1, v[(i + 1) & 1]);
+          if (t.n0 + c0 < P.Cout) process(v[i & 1], c0);  // chunks entirely past Cout carry no output
         }
       }
-      // all tcgen05.ld of this warp have completed (wait::ld inside tmem_ld32): hand the buffer back
+      // every tcgen05.ld of this warp has completed: hand the accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
@@ -725,6 +739,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   P.tilesW = (Win + P.BW - 1) / P.BW;
   P.tilesH = (Hin + P.BH - 1) / P.BH;
   int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
+  if (BN == 256 && Cout % 256 != 0 && Cout % 128 == 0) BN = 128;  // e.g. to_qkv (384): no half-empty N tile
   d->BN = BN;
   d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
   d->tiles_m = P.tilesW * P.tilesH * B * nphases;
@@ -813,10 +828,10 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
   if (g_persist) {
     const unsigned g = (unsigned)(d->num_tiles < g_num_sms ? d->num_tiles : g_num_sms);
     switch (d->BN) {
-      case 32: conv_tc_persist_kernel<32><<<g, 192, TcCfgP<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
-      case 64: conv_tc_persist_kernel<64><<<g, 192, TcCfgP<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
-      case 128: conv_tc_persist_kernel<128><<<g, 192, TcCfgP<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
-      default: conv_tc_persist_kernel<256><<<g, 192, TcCfgP<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+      case 32: conv_tc_persist_kernel<32><<<g, 320, TcCfgP<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+      case 64: conv_tc_persist_kernel<64><<<g, 320, TcCfgP<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+      case 128: conv_tc_persist_kernel<128><<<g, 320, TcCfgP<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+      default: conv_tc_persist_kernel<256><<<g, 320, TcCfgP<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
     }
     return 1;
   }
