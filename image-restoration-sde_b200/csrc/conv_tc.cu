@@ -46,6 +46,7 @@ struct TcParams {
   int tma_store;        // persistent kernel: bf16 NHWC output through smem + TMA bulk store
   int qsm;              // LinearAttention q: softmax over each 32-channel head * 32^-0.5 for output channels < 128
   int w_per_image;      // weights tensor is [B][Cout][Cin]: third TMA coordinate = image index
+  unsigned long long* dbg;  // optional [grid][8] cycle counters (IRSDE_TC_DEBUG=1)
   const bf16* res;
   int res_pitch;
   const float* bias;
@@ -114,11 +115,11 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
 
 // SM100 shared-memory matrix descriptor: K-major operand, 128B swizzle, rows of 128 bytes,
 // 8-row core groups 1024 B apart (SBO), descriptor version 1.
-__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t sbo_bytes = 1024) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);        // start address
   d |= (uint64_t)(0) << 16;                           // leading byte offset (unused for swizzled K-major)
-  d |= (uint64_t)((1024 >> 4) & 0x3FFF) << 32;        // stride byte offset
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;   // stride byte offset between 8-row groups
   d |= (uint64_t)1 << 46;                             // version = 1 (sm_100)
   d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
   return d;
@@ -361,16 +362,43 @@ __global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CU
 // the smem ring is as deep as 192 KB allows (BN=256: 4, BN=128: 6, BN<=64: 8 stages) to cover TMA
 // latency, and the prologue (barrier init, TMEM alloc, descriptor prefetch) is paid once per SM.
 // =====================================================================================================
-template <int BN>
+//
+// PATCH mode (3x3 stride-1 convs): the tile is 8 x 16 pixels and, per 64-channel chunk, ONE TMA box of the
+// (8+2) x (16+2) halo patch is loaded and reused by all 9 taps: tap (dh,dw) is the same shared-memory patch
+// addressed through a UMMA descriptor whose start is shifted by ((dh+1)*10 + (dw+1)) pixel rows (128 B each)
+// and whose 8-row-group stride (SBO) is the patch row pitch (10 * 128 B).  The 128B swizzle is a function of
+// the shared-memory address, so TMA's write pattern and the shifted UMMA reads agree.  A-operand L2->smem
+// traffic drops from 9 x 16 KB to 22.5 KB per chunk; only the weight tiles stream through the ring.
+constexpr int PATCH_W = 10, PATCH_H = 18;
+constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;   // 23040
+constexpr int PATCH_STRIDE = 24 * 1024;                // per-buffer stride (1024-aligned)
+
+template <int BN, bool PATCH>
 struct TcCfgP {
-  static constexpr int STAGES = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int B_STAGE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
+  // non-PATCH: G consecutive k-iterations (64-channel chunks) share one full/empty barrier round, which amortises the
+  // mbarrier wait + tcgen05.commit of the single MMA-issuing thread over 4*G MMAs (matters for narrow N tiles)
+  static constexpr int G = 1;  // measured: G=2 trades issue overhead for coarser prefetch granularity; no net gain
+  static constexpr int STAGES = PATCH ? (BN == 256 ? 4 : (BN == 128 ? 8 : 12)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
+  static constexpr int STAGE_BYTES = PATCH ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;  // per k-iteration
+  static constexpr int A_BYTES = PATCH ? 2 * PATCH_STRIDE : STAGES * G * A_STAGE_BYTES;   // patch double buffer | A ring
   static constexpr int EPI_FLOATS = 3 * BN;
   static constexpr int STG_BYTES = 8 * 2048;  // per epilogue warp: one 32 rows x 64 B staging tile for TMA stores
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 256;
+  static constexpr int SMEM_BYTES = 1024 + A_BYTES + STAGES * G * B_STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 512;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
+
+// One elected lane of a converged warp (the compiler recognises elect.sync and emits straight-line uniform
+// datapath code for the UTMA / UTCHMMA instructions under it, instead of per-active-thread ELECT loops).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -404,26 +432,39 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
   return t;
 }
 
-template <int BN>
+#define DBG_WAIT(ctr, bar, par)                 \
+  do {                                          \
+    if (P.dbg) {                                \
+      long long _t0 = clock64();                \
+      mbar_wait(bar, par);                      \
+      ctr += clock64() - _t0;                   \
+    } else {                                    \
+      mbar_wait(bar, par);                      \
+    }                                           \
+  } while (0)
+
+template <int BN, bool PATCH>
 __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                  const __grid_constant__ OutMaps map_o,
                                                                  const __grid_constant__ TcParams P, int tiles_m,
                                                                  int num_tiles) {
-  using Cfg = TcCfgP<BN>;
+  using Cfg = TcCfgP<BN, PATCH>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  uint8_t* smem_stg = smem + STAGES * Cfg::STAGE_BYTES;  // 1024-aligned (stages are multiples of 1024)
+  uint8_t* smem_a = smem;                       // A ring, or the two halo-patch buffers in PATCH mode
+  uint8_t* smem_b = smem + Cfg::A_BYTES;
+  uint8_t* smem_stg = smem_b + STAGES * Cfg::G * Cfg::B_STAGE_BYTES;  // 1024-aligned
   float* s_epi = reinterpret_cast<float*>(smem_stg + Cfg::STG_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::EPI_FLOATS);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2] accumulator ready
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] accumulator drained
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 4);
+  uint64_t* pfull_bar = bars + 2 * STAGES + 4;   // [2] halo patch landed (PATCH)
+  uint64_t* pempty_bar = bars + 2 * STAGES + 6;  // [2] halo patch consumed (PATCH)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KI = P.ntaps * P.kchunks;
@@ -436,6 +477,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
+      mbar_init(&pfull_bar[a], 1);
+      mbar_init(&pempty_bar[a], 1);
     }
     fence_barrier_init();
   }
@@ -456,48 +499,121 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int it = 0;
+    // ================= TMA producer (whole warp loops; one elected lane issues) =================
+    {
+      int it = 0, pc = 0;
+      long long w_prod = 0, t_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile, tiles_m, BN);
-        for (int tap = 0; tap < P.ntaps; ++tap) {
-          const int dh = P.taps[tap].dh + (P.nphases == 4 ? t.py : 0);
-          const int dw = P.taps[tap].dw + (P.nphases == 4 ? t.px : 0);
-          const int plane = P.taps[tap].plane;
-          for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
+        if constexpr (PATCH) {
+          for (int kc = 0; kc < P.kchunks; ++kc, ++pc) {
+            const int pb = pc & 1;
+            if (pc >= 2) DBG_WAIT(w_prod, &pempty_bar[pb], ((pc >> 1) - 1) & 1);
+            if (elect_one()) {
+              mbar_expect_tx(&pfull_bar[pb], PATCH_BYTES);
+              tma_load_5d(smem_a + pb * PATCH_STRIDE, &map_a, &pfull_bar[pb], kc * 64, t.w0 - 1, t.h0 - 1, t.b, 0);
+            }
+            __syncwarp();
+            for (int tap = 0; tap < 9; ++tap, ++it) {
+              const int s = it % STAGES;
+              if (it >= STAGES) DBG_WAIT(w_prod, &empty_bar[s], ((it / STAGES) - 1) & 1);
+              if (elect_one()) {
+                mbar_expect_tx(&full_bar[s], Cfg::B_STAGE_BYTES);
+                tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0, tap);
+              }
+              __syncwarp();
+            }
+          }
+        } else {
+          constexpr int G = Cfg::G;
+          for (int g0 = 0; g0 < KI; g0 += G, ++it) {
             const int s = it % STAGES;
-            if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-            mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-            tma_load_5d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, t.w0 + dw, t.h0 + dh, t.b, plane);
-            tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0,
-                        t.phase * P.ntaps + tap + (P.w_per_image ? t.b : 0));
+            if (it >= STAGES) DBG_WAIT(w_prod, &empty_bar[s], ((it / STAGES) - 1) & 1);
+            if (elect_one()) {
+              const int n = (KI - g0) < G ? (KI - g0) : G;
+              mbar_expect_tx(&full_bar[s], n * Cfg::STAGE_BYTES);
+#pragma unroll
+              for (int j = 0; j < G; ++j) {
+                if (j < n) {
+                  const int ki = g0 + j, tap = ki / P.kchunks, kc = ki - tap * P.kchunks;
+                  const int dh = P.taps[tap].dh + (P.nphases == 4 ? t.py : 0);
+                  const int dw = P.taps[tap].dw + (P.nphases == 4 ? t.px : 0);
+                  tma_load_5d(smem_a + (s * G + j) * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, t.w0 + dw, t.h0 + dh, t.b,
+                              P.taps[tap].plane);
+                  tma_load_3d(smem_b + (s * G + j) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0,
+                              t.phase * P.ntaps + tap + (P.w_per_image ? t.b : 0));
+                }
+              }
+            }
+            __syncwarp();
           }
         }
       }
+      if (P.dbg && lane == 0) { P.dbg[blockIdx.x * 8 + 0] = (unsigned long long)w_prod; P.dbg[blockIdx.x * 8 + 1] = (unsigned long long)(clock64() - t_start); }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp loops; one elected lane issues) =================
+    {
       const uint32_t idesc = make_idesc_bf16(128, BN);
-      int it = 0, lt = 0;
+      int it = 0, lt = 0, pc = 0;
+      long long w_full = 0, w_tempty = 0, t_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
         const int acc = lt & 1;
-        if (lt >= 2) mbar_wait(&tempty_bar[acc], ((lt >> 1) - 1) & 1);  // epilogue drained this buffer
+        if (lt >= 2) DBG_WAIT(w_tempty, &tempty_bar[acc], ((lt >> 1) - 1) & 1);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        for (int ki = 0; ki < KI; ++ki, ++it) {
-          const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
-          tc_fence_after();
-          const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
-          const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
+        if constexpr (PATCH) {
+          for (int kc = 0; kc < P.kchunks; ++kc, ++pc) {
+            const int pb = pc & 1;
+            DBG_WAIT(w_full, &pfull_bar[pb], (pc >> 1) & 1);
+            const uint32_t patch = smem_u32(smem_a + pb * PATCH_STRIDE);
+            for (int tap = 0; tap < 9; ++tap, ++it) {
+              const int s = it % STAGES;
+              DBG_WAIT(w_full, &full_bar[s], (it / STAGES) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                const int dh = P.taps[tap].dh, dw = P.taps[tap].dw;
+                const uint64_t adesc = make_sw128_desc(patch + (uint32_t)(((dh + 1) * PATCH_W + dw + 1) * 128), PATCH_W * 128);
+                const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ki > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&empty_bar[s]);
+                if (tap == 8) umma_commit(&pempty_bar[pb]);  // all 9 taps of this chunk issued
+              }
+              __syncwarp();
+            }
+          }
+        } else {
+          constexpr int G = Cfg::G;
+          for (int g0 = 0; g0 < KI; g0 += G, ++it) {
+            const int s = it % STAGES;
+            DBG_WAIT(w_full, &full_bar[s], (it / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const int n = (KI - g0) < G ? (KI - g0) : G;
+#pragma unroll
+              for (int j = 0; j < G; ++j) {
+                if (j < n) {
+                  const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + (s * G + j) * A_STAGE_BYTES));
+                  const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + (s * G + j) * Cfg::B_STAGE_BYTES));
+#pragma unroll
+                  for (int k = 0; k < 4; ++k)
+                    umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (g0 + j > 0 || k > 0) ? 1u : 0u);
+                }
+              }
+              umma_commit(&empty_bar[s]);
+            }
+            __syncwarp();
+          }
         }
-        umma_commit(&tfull_bar[acc]);
+        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        __syncwarp();
+      }
+      if (P.dbg && lane == 0) {
+        P.dbg[blockIdx.x * 8 + 2] = (unsigned long long)w_full;
+        P.dbg[blockIdx.x * 8 + 3] = (unsigned long long)w_tempty;
+        P.dbg[blockIdx.x * 8 + 4] = (unsigned long long)(clock64() - t_start);
       }
     }
   } else {
@@ -511,6 +627,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     const int trow = P.t_ptr ? *P.t_ptr : 0;
     const bool affine = (P.ss != nullptr) || (P.bias != nullptr);
     uint8_t* stg = smem_stg + (warp - 2) * 2048;
+    long long w_tfull = 0, t_start = clock64();
     int lt = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const TileCoord t = decode_tile(P, tile, tiles_m, BN);
@@ -615,7 +732,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
         }
       };
 
-      mbar_wait(&tfull_bar[acc], (lt >> 1) & 1);
+      DBG_WAIT(w_tfull, &tfull_bar[acc], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
       constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp
@@ -637,6 +754,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
     if (lane == 0) bulk_wait_all();  // staging smem must stay valid until the last bulk store has read it
+    if (P.dbg && threadIdx.x == 64) {
+      P.dbg[blockIdx.x * 8 + 5] = (unsigned long long)w_tfull;
+      P.dbg[blockIdx.x * 8 + 6] = (unsigned long long)(clock64() - t_start);
+      P.dbg[blockIdx.x * 8 + 7] = (unsigned long long)lt;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -648,6 +770,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 int g_num_sms = 148;
 bool g_persist = true;
 bool g_tma_store = true;
+bool g_patch = false;  // opt-in (IRSDE_TC_PATCH=1): measured slower than per-tap boxes, see DESIGN.md
 
 }  // namespace
 
@@ -658,6 +781,7 @@ struct TcConvDesc {
   int BN;
   dim3 grid;
   int tiles_m, num_tiles;
+  bool patch;
 };
 
 bool tc_init(std::string* err) {
@@ -674,10 +798,14 @@ bool tc_init(std::string* err) {
   cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, false>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, true>::SMEM_BYTES);
   {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);
@@ -686,6 +814,8 @@ bool tc_init(std::string* err) {
     g_persist = !(e && e[0] == '0');
     e = getenv("IRSDE_TC_TMA_STORE");
     g_tma_store = !(e && e[0] == '0');
+    e = getenv("IRSDE_TC_PATCH");
+    g_patch = (e && e[0] == '1');
   }
   cudaError_t le = cudaGetLastError();
   if (le != cudaSuccess) {
@@ -727,6 +857,10 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   P.w_per_image = (flags & TC_FLAG_W_PER_IMAGE) ? 1 : 0;
   if (P.w_per_image && (ntaps != 1 || nphases != 1)) return bad("per-image weights need a 1x1 conv");
   if ((P.qsm || P.w_per_image) && !(g_persist && g_tma_store)) return bad("fused attention epilogues need the persistent TMA-store kernel");
+  // PATCH mode: plain 3x3 / stride 1 / pad 1 on the persistent kernel
+  bool patch = g_persist && g_patch && nphases == 1 && planes == 1 && ntaps == 9;
+  for (int i = 0; patch && i < 9; ++i) patch = taps[i].dh == i / 3 - 1 && taps[i].dw == i % 3 - 1 && taps[i].plane == 0;
+  d->patch = patch;
   // tile shape: BW x BH = 128 pixels, minimise padded work
   long long best = -1;
   for (int bw = 128; bw >= 8; bw >>= 1) {
@@ -734,6 +868,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
     long long cost = (long long)((Win + bw - 1) / bw) * bw * ((Hin + bh - 1) / bh) * bh;
     if (best < 0 || cost < best) { best = cost; P.BW = bw; P.BH = bh; }
   }
+  if (patch) { P.BW = 8; P.BH = 16; }
   P.logBW = 0;
   while ((1 << P.logBW) < P.BW) P.logBW++;
   P.tilesW = (Win + P.BW - 1) / P.BW;
@@ -758,6 +893,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
       strides[3] = strides[2] * B;
     }
     cuuint32_t box[5] = {64, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1, 1};
+    if (patch) { box[1] = PATCH_W; box[2] = PATCH_H; }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(&d->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in, dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -827,11 +963,40 @@ void tc_conv_set_runtime(TcConvDesc* d, const float* ss, const int* t_ptr, int s
 int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
   if (g_persist) {
     const unsigned g = (unsigned)(d->num_tiles < g_num_sms ? d->num_tiles : g_num_sms);
-    switch (d->BN) {
-      case 32: conv_tc_persist_kernel<32><<<g, 320, TcCfgP<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
-      case 64: conv_tc_persist_kernel<64><<<g, 320, TcCfgP<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
-      case 128: conv_tc_persist_kernel<128><<<g, 320, TcCfgP<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
-      default: conv_tc_persist_kernel<256><<<g, 320, TcCfgP<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles); break;
+    static unsigned long long* dbg_dev = nullptr;
+    const char* dbg_env = getenv("IRSDE_TC_DEBUG");
+    const bool dbg = dbg_env && dbg_env[0] == '1';
+    if (dbg) {
+      if (!dbg_dev) cudaMalloc(&dbg_dev, 256 * 8 * sizeof(unsigned long long));
+      cudaMemsetAsync(dbg_dev, 0, 256 * 8 * sizeof(unsigned long long), st);
+    }
+    d->P.dbg = dbg ? dbg_dev : nullptr;
+#define TC_LAUNCH(BNV, PV) \
+  conv_tc_persist_kernel<BNV, PV><<<g, 320, TcCfgP<BNV, PV>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles)
+    if (d->patch) {
+      switch (d->BN) {
+        case 32: TC_LAUNCH(32, true); break;
+        case 64: TC_LAUNCH(64, true); break;
+        case 128: TC_LAUNCH(128, true); break;
+        default: TC_LAUNCH(256, true); break;
+      }
+    } else {
+      switch (d->BN) {
+        case 32: TC_LAUNCH(32, false); break;
+        case 64: TC_LAUNCH(64, false); break;
+        case 128: TC_LAUNCH(128, false); break;
+        default: TC_LAUNCH(256, false); break;
+      }
+    }
+#undef TC_LAUNCH
+    if (dbg) {
+      unsigned long long h[256 * 8];
+      cudaStreamSynchronize(st);
+      cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
+      double a[8] = {0};
+      for (unsigned i = 0; i < g; ++i) for (int k = 0; k < 8; ++k) a[k] += (double)h[i * 8 + k] / g;
+      fprintf(stderr, "TCDBG BN=%d patch=%d grid=%u tiles=%d ntaps=%d kch=%d | prod wait %.0f / %.0f | mma wait full %.0f tempty %.0f / %.0f | epi wait tfull %.0f / %.0f (tiles/cta %.1f)\n",
+              d->BN, (int)d->patch, g, d->num_tiles, d->P.ntaps, d->P.kchunks, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
     }
     return 1;
   }
