@@ -2,6 +2,7 @@
 // (module_util.py:150-178) and the full softmax Attention of the denoising-sde variant (:182-204).
 // All loads/stores are 128-bit vectors over the NHWC channel dimension; math is fp32.
 #include <math.h>
+#include <string.h>
 
 #include "common.cuh"
 
@@ -56,7 +57,7 @@ template <typename T, int MAXV>
 __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict__ x, int x_pitch,
                                                             const float* __restrict__ g, const T* __restrict__ res,
                                                             int res_pitch, T* __restrict__ out, int out_pitch,
-                                                            long long npix, int C, int lpp) {
+                                                            long long npix, int C, int lpp, LnMod mod) {
   constexpr int N = VecIO<T>::N;
   const int lane = threadIdx.x & 31;
   const int ppw = 32 / lpp;
@@ -93,6 +94,8 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict_
   for (int o = lpp >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
   const float rstd = 1.0f / sqrtf(q / (float)C + 1e-5f);
   if (!valid) return;
+  const float* mrow = nullptr;  // NAFBlock time modulation: y * (scale + 1) + shift  (DenoisingNAFNet_arch.py:62-63,75-76)
+  if (mod.ss) mrow = mod.ss + (long long)((mod.t_ptr ? *mod.t_ptr : 0) + (int)(pix / mod.pix_per_img) * mod.img_stride) * mod.S;
 #pragma unroll
   for (int k = 0; k < MAXV; ++k) {
     const int i = sub + k * lpp;
@@ -105,6 +108,10 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict_
         y[j + 1] = (v[k][j + 1] - mean) * rstd * gg.y;
         y[j + 2] = (v[k][j + 2] - mean) * rstd * gg.z;
         y[j + 3] = (v[k][j + 3] - mean) * rstd * gg.w;
+      }
+      if (mrow) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) y[j] = y[j] * (mrow[mod.off_scale + i * N + j] + 1.0f) + mrow[mod.off_shift + i * N + j];
       }
       if (res) {
         VecIO<T>::load(res + pix * res_pitch + i * N, r);
@@ -120,7 +127,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict_
 template <typename T>
 __global__ void layernorm_scalar_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
                                         const T* __restrict__ res, int res_pitch, T* __restrict__ out, int out_pitch,
-                                        long long npix, int C) {
+                                        long long npix, int C, LnMod mod) {
   int lane = threadIdx.x & 31;
   long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= npix) return;
@@ -137,8 +144,11 @@ __global__ void layernorm_scalar_kernel(const T* __restrict__ x, int x_pitch, co
   float rstd = 1.0f / sqrtf(v / (float)C + 1e-5f);
   T* orow = out + pix * out_pitch;
   const T* rr = res ? res + pix * res_pitch : nullptr;
+  const float* mrow = nullptr;
+  if (mod.ss) mrow = mod.ss + (long long)((mod.t_ptr ? *mod.t_ptr : 0) + (int)(pix / mod.pix_per_img) * mod.img_stride) * mod.S;
   for (int c = lane; c < C; c += 32) {
     float y = (to_f(xr[c]) - mean) * rstd * g[c];
+    if (mrow) y = y * (mrow[mod.off_scale + c] + 1.0f) + mrow[mod.off_shift + c];
     if (rr) y += to_f(rr[c]);
     orow[c] = from_f<T>(y);
   }
@@ -146,7 +156,11 @@ __global__ void layernorm_scalar_kernel(const T* __restrict__ x, int x_pitch, co
 
 template <typename T>
 void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int res_pitch, T* out, int out_pitch,
-                      long long npix, int C, cudaStream_t st) {
+                      long long npix, int C, cudaStream_t st, const LnMod* modp) {
+  LnMod mod;
+  memset(&mod, 0, sizeof mod);
+  if (modp) mod = *modp;
+  if (mod.pix_per_img <= 0) mod.pix_per_img = 1;
   constexpr int N = VecIO<T>::N;
   bool vec_ok = C % N == 0 && x_pitch % N == 0 && out_pitch % N == 0 && ((uintptr_t)x % 16 == 0) &&
                 ((uintptr_t)out % 16 == 0) && ((uintptr_t)g % 16 == 0) &&
@@ -158,14 +172,14 @@ void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int
   if (!vec_ok || per_lane > 16) {
     const int warps = 8;
     layernorm_scalar_kernel<T><<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch,
-                                                                                            out, out_pitch, npix, C);
+                                                                                            out, out_pitch, npix, C, mod);
     return;
   }
   const int warps = 8;
   long long pix_per_block = (long long)warps * (32 / lpp);
   unsigned grid = (unsigned)((npix + pix_per_block - 1) / pix_per_block);
 #define LN_LAUNCH(MV) \
-  layernorm_vec_kernel<T, MV><<<grid, warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch, out, out_pitch, npix, C, lpp)
+  layernorm_vec_kernel<T, MV><<<grid, warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch, out, out_pitch, npix, C, lpp, mod)
   if (per_lane <= 1) LN_LAUNCH(1);
   else if (per_lane <= 2) LN_LAUNCH(2);
   else if (per_lane <= 4) LN_LAUNCH(4);
@@ -174,9 +188,9 @@ void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int
 #undef LN_LAUNCH
 }
 template void launch_layernorm<float>(const float*, int, const float*, const float*, int, float*, int, long long, int,
-                                      cudaStream_t);
+                                      cudaStream_t, const LnMod*);
 template void launch_layernorm<bf16>(const bf16*, int, const float*, const bf16*, int, bf16*, int, long long, int,
-                                     cudaStream_t);
+                                     cudaStream_t, const LnMod*);
 
 // =============================================================================================
 // LinearAttention core (module_util.py:163-177).  heads=4, dim_head=32 (fixed by the reference).

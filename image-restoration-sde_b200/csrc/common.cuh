@@ -37,6 +37,7 @@ struct Epilogue {
   int ss_S;               // row length of the table
   int ss_off;             // offset of this block's (scale[Cout], shift[Cout]) inside a row
   int ss_img_stride;      // rows per image (0 = shared time, 1 = per-image time)
+  const float* mult_vec;  // per-output-channel multiplier (NAFBlock beta / gamma) or null; overrides the table's scale
   int silu;               // apply SiLU after modulation
   const void* res;        // residual view (same dtype as output) or null
   int res_pitch;
@@ -64,15 +65,39 @@ void launch_conv_simt(const ConvGeom& g, const T* in, int in_pitch, const float*
 template <typename T>
 void launch_prep_input(const float* xt, const float* cond, T* out, int B, int C, int H, int W, int Hp, int Wp,
                        int out_pitch, int conditional, cudaStream_t st, int pad_top = 0, int pad_left = 0, int row_pix = 0,
-                       int img_rows = 0);
+                       int img_rows = 0, int zero_pad = 0);
 template <typename T>
 void launch_nchw_to_nhwc(const float* in, T* out, int B, int C, int H, int W, int out_pitch, cudaStream_t st);
 template <typename T>
 void launch_nhwc_to_nchw(const T* in, int in_pitch, float* out, int B, int C, int H, int W, cudaStream_t st);
-// channel LayerNorm (eps 1e-5) * g (+ residual)
+// channel LayerNorm (eps 1e-5) * g [* (scale+1) + shift from the time table] (+ residual)
+struct LnMod {
+  const float* ss;     // time table base or null
+  const int* t_ptr;    // device row index (null => 0)
+  int S, off_scale, off_shift, img_stride, pix_per_img;
+};
 template <typename T>
 void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int res_pitch, T* out, int out_pitch,
-                      long long npix, int C, cudaStream_t st);
+                      long long npix, int C, cudaStream_t st, const LnMod* mod = nullptr);
+// ---- NAFNet kernels (nafnet.cu)
+int dwgate_chunks(int H, int W);
+template <typename T>
+void launch_dwgate(const T* x, int x_pitch, const float* w, const float* bias, T* gate, int g_pitch, float* partial, int B,
+                   int H, int W, int c, cudaStream_t st);
+void launch_sca(const float* partial, const float* w, const float* bias, float* sca, int B, int c, int nchunks, int N, cudaStream_t st);
+template <typename T>
+void launch_scale_channels(T* x, int pitch, const float* sca, int B, int N, int c, cudaStream_t st);
+template <typename T>
+void launch_simple_gate(const T* x, int x_pitch, T* out, int o_pitch, long long npix, int c, cudaStream_t st);
+template <typename T>
+void launch_pixel_shuffle_add(const T* in, int in_pitch, const T* skip, int s_pitch, T* out, int o_pitch, int B, int h, int w, int q,
+                              cudaStream_t st);
+template <typename T>
+void launch_add(const T* a, int a_pitch, const T* b, int b_pitch, T* out, int o_pitch, long long npix, int c, cudaStream_t st);
+void launch_naf_time_gate(const float* times, int rows, int width, const float* w1, const float* b1, const float* w2,
+                          const float* b2, float* tgate, cudaStream_t st);
+// table[r][j] = dot(wall[j][0..td), tvec[r][0..td)) + ball[j]
+void launch_time_rows(const float* tvec, int rows, int td, const float* wall, const float* ball, int S, float* table, cudaStream_t st);
 // linear attention: qkv [B,N,384] -> ctx [B,4,32,32] (fp32) -> hidden [B,N,128]
 template <typename T>
 void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,

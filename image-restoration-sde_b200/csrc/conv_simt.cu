@@ -163,6 +163,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvGeom g, const T* __r
           const float* row = ep.ss + (long long)(trow + b * ep.ss_img_stride) * ep.ss_S + ep.ss_off;
           x = x * (row[n] + 1.0f) + row[g.Cout + n];
         }
+        if (ep.mult_vec) x *= ep.mult_vec[n];
         if (ep.silu) x = silu_f(x);
       }
       v[j] = x;

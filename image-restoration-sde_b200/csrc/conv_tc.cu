@@ -50,6 +50,7 @@ struct TcParams {
   const bf16* res;
   int res_pitch;
   const float* bias;
+  const float* mult_vec;
   const float* ss;
   const int* t_ptr;
   int ss_S, ss_off, ss_img_stride, silu;
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     const int half = (warp - 2) >> 2;
     const int m = quad * 32 + lane;
     const int trow = P.t_ptr ? *P.t_ptr : 0;
-    const bool affine = (P.ss != nullptr) || (P.bias != nullptr);
+    const bool affine = (P.ss != nullptr) || (P.bias != nullptr) || (P.mult_vec != nullptr);
     uint8_t* stg = smem_stg + (warp - 2) * 2048;
     long long w_tfull = 0, t_start = clock64();
     int lt = 0;
@@ -640,6 +641,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
           float mult = 1.f, add = 0.f, bias = 0.f;
           if (n < P.Cout) {
             if (ssrow) { mult = ssrow[n] + 1.0f; add = ssrow[P.Cout + n]; }
+            if (P.mult_vec) mult *= P.mult_vec[n];
             if (P.bias) bias = P.bias[n];
           }
           s_epi[j] = mult; s_epi[BN + j] = bias * mult + add;  // (x + bias) * mult + add == x * mult + (bias * mult + add)
@@ -850,7 +852,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   P.Hout = Hout; P.Wout = Wout; P.os = nphases == 4 ? 2 : 1;
   P.out = out; P.out_pitch = out_pitch;
   P.res = (const bf16*)ep.res; P.res_pitch = ep.res_pitch;
-  P.bias = ep.bias; P.ss = ep.ss; P.t_ptr = ep.t_ptr; P.ss_S = ep.ss_S; P.ss_off = ep.ss_off;
+  P.bias = ep.bias; P.mult_vec = ep.mult_vec; P.ss = ep.ss; P.t_ptr = ep.t_ptr; P.ss_S = ep.ss_S; P.ss_off = ep.ss_off;
   P.ss_img_stride = ep.ss_img_stride; P.silu = ep.silu;
   for (int i = 0; i < ntaps; ++i) P.taps[i] = taps[i];
   P.qsm = (flags & TC_FLAG_QSOFTMAX) ? 1 : 0;

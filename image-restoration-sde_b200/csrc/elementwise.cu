@@ -14,7 +14,7 @@ namespace irsde {
 template <typename T>
 __global__ void prep_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond, T* __restrict__ out,
                                   int B, int C, int H, int W, int Hp, int Wp, int pitch, int conditional,
-                                  int pad_top, int pad_left, int row_pix, int img_rows) {
+                                  int pad_top, int pad_left, int row_pix, int img_rows, int zero_pad) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Hp * Wp;
   if (idx >= total) return;
@@ -25,11 +25,12 @@ __global__ void prep_input_kernel(const float* __restrict__ xt, const float* __r
   int w = wp < W ? wp : 2 * (W - 1) - wp;
   // destination pixel inside an optionally zero-bordered buffer [B][img_rows][row_pix][pitch]
   T* o = out + (((long long)b * img_rows + hp + pad_top) * row_pix + wp + pad_left) * pitch;
+  const bool zp = zero_pad && (hp >= H || wp >= W);  // NAFNet pads with zeros (DenoisingNAFNet_arch.py:183-188)
   for (int c = 0; c < C; ++c) {
     long long s = (((long long)b * C + c) * H + h) * W + w;
-    float xv = xt[s];
+    float xv = zp ? 0.f : xt[s];
     if (conditional) {
-      float cv = cond[s];
+      float cv = zp ? 0.f : cond[s];
       o[c] = from_f<T>(__fsub_rn(xv, cv));
       o[C + c] = from_f<T>(cv);
     } else {
@@ -42,16 +43,16 @@ __global__ void prep_input_kernel(const float* __restrict__ xt, const float* __r
 template <typename T>
 void launch_prep_input(const float* xt, const float* cond, T* out, int B, int C, int H, int W, int Hp, int Wp,
                        int out_pitch, int conditional, cudaStream_t st, int pad_top, int pad_left, int row_pix,
-                       int img_rows) {
+                       int img_rows, int zero_pad) {
   long long total = (long long)B * Hp * Wp;
   if (row_pix == 0) { row_pix = Wp; img_rows = Hp; }
   prep_input_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xt, cond, out, B, C, H, W, Hp, Wp, out_pitch,
-                                                                         conditional, pad_top, pad_left, row_pix, img_rows);
+                                                                         conditional, pad_top, pad_left, row_pix, img_rows, zero_pad);
 }
 template void launch_prep_input<float>(const float*, const float*, float*, int, int, int, int, int, int, int, int,
-                                       cudaStream_t, int, int, int, int);
+                                       cudaStream_t, int, int, int, int, int);
 template void launch_prep_input<bf16>(const float*, const float*, bf16*, int, int, int, int, int, int, int, int,
-                                      cudaStream_t, int, int, int, int);
+                                      cudaStream_t, int, int, int, int, int);
 
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int C, int H, int W,
@@ -141,6 +142,10 @@ __global__ void time_table_kernel(const float* __restrict__ temb_silu, int td, c
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   if (lane == 0) table[(long long)row * S + j] = s + ball[j];
+}
+
+void launch_time_rows(const float* tvec, int rows, int td, const float* wall, const float* ball, int S, float* table, cudaStream_t st) {
+  time_table_kernel<<<dim3((S + 7) / 8, rows), 256, 0, st>>>(tvec, td, wall, ball, S, table);
 }
 
 void launch_time_table(const float* times, int rows, int nf, const float* w1, const float* b1, const float* w2,

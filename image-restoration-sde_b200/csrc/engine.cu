@@ -10,6 +10,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <map>
 #include <string>
@@ -69,8 +70,16 @@ struct Plan {
 };
 }  // namespace
 
+struct NafCfg {
+  bool on = false;
+  int img_channel = 0, width = 0, middle = 0, n_enc = 0, n_dec = 0;
+  int enc[8] = {0}, dec[8] = {0};
+  bool latent = false;
+};
+
 struct irsde_ctx {
   irsde_config cfg;
+  NafCfg naf;
   mutable std::string err;
   std::map<std::string, RawTensor> raw;
   bool finalized = false;
@@ -224,6 +233,76 @@ struct ParamSpec {
   std::string name;
   std::vector<int64_t> shape;
 };
+
+// NAFBlocks of ConditionalNAFNet in a fixed order (prefix, channels)   DenoisingNAFNet_arch.py:111-141
+struct NafBlockInfo {
+  std::string pre;
+  int c;
+};
+std::vector<NafBlockInfo> naf_blocks(const NafCfg& n) {
+  std::vector<NafBlockInfo> v;
+  char b[64];
+  int chan = n.width;
+  for (int i = 0; i < n.n_enc; ++i) {
+    for (int j = 0; j < n.enc[i]; ++j) { snprintf(b, sizeof b, "encoders.%d.%d.", i, j); v.push_back({b, chan}); }
+    chan *= 2;
+  }
+  for (int j = 0; j < n.middle; ++j) { snprintf(b, sizeof b, "middle_blks.%d.", j); v.push_back({b, chan}); }
+  for (int i = 0; i < n.n_dec; ++i) {
+    chan /= 2;
+    for (int j = 0; j < n.dec[i]; ++j) { snprintf(b, sizeof b, "decoders.%d.%d.", i, j); v.push_back({b, chan}); }
+  }
+  return v;
+}
+std::vector<ParamSpec> naf_param_specs(const NafCfg& n) {
+  std::vector<ParamSpec> v;
+  int64_t w = n.width, td = 4 * w, ic = n.img_channel;
+  v.push_back({"time_mlp.1.weight", {2 * td, w}});
+  v.push_back({"time_mlp.1.bias", {2 * td}});
+  v.push_back({"time_mlp.3.weight", {td, td}});
+  v.push_back({"time_mlp.3.bias", {td}});
+  v.push_back({"intro.weight", {w, 2 * ic, 3, 3}});
+  v.push_back({"intro.bias", {w}});
+  v.push_back({"ending.weight", {ic, w, 3, 3}});
+  v.push_back({"ending.bias", {ic}});
+  for (auto& blk : naf_blocks(n)) {
+    int64_t c = blk.c;
+    const std::string& p = blk.pre;
+    v.push_back({p + "beta", {1, c, 1, 1}});
+    v.push_back({p + "gamma", {1, c, 1, 1}});
+    v.push_back({p + "mlp.1.weight", {4 * c, td / 2}});
+    v.push_back({p + "mlp.1.bias", {4 * c}});
+    v.push_back({p + "conv1.weight", {2 * c, c, 1, 1}});
+    v.push_back({p + "conv1.bias", {2 * c}});
+    v.push_back({p + "conv2.weight", {2 * c, 1, 3, 3}});
+    v.push_back({p + "conv2.bias", {2 * c}});
+    v.push_back({p + "conv3.weight", {c, c, 1, 1}});
+    v.push_back({p + "conv3.bias", {c}});
+    v.push_back({p + "sca.1.weight", {c, c, 1, 1}});
+    v.push_back({p + "sca.1.bias", {c}});
+    v.push_back({p + "conv4.weight", {2 * c, c, 1, 1}});
+    v.push_back({p + "conv4.bias", {2 * c}});
+    v.push_back({p + "conv5.weight", {c, c, 1, 1}});
+    v.push_back({p + "conv5.bias", {c}});
+    v.push_back({p + "norm1.g", {1, c, 1, 1}});
+    v.push_back({p + "norm2.g", {1, c, 1, 1}});
+  }
+  char b[64];
+  int64_t chan = w << n.n_enc;
+  for (int i = 0; i < n.n_dec; ++i) {
+    snprintf(b, sizeof b, "ups.%d.0.weight", i);
+    v.push_back({b, {chan * 2, chan, 1, 1}});
+    chan /= 2;
+  }
+  chan = w;
+  for (int i = 0; i < n.n_enc; ++i) {
+    snprintf(b, sizeof b, "downs.%d.", i);
+    v.push_back({std::string(b) + "weight", {chan * 2, chan, 2, 2}});
+    v.push_back({std::string(b) + "bias", {chan * 2}});
+    chan *= 2;
+  }
+  return v;
+}
 std::vector<ParamSpec> param_specs(const irsde_config& c) {
   std::vector<ParamSpec> v;
   int64_t nf = c.nf, td = 4 * nf;
@@ -294,6 +373,7 @@ struct Builder {
   std::string err;
   std::multimap<size_t, void*> free_tmp;
   std::map<void*, size_t> tmp_size;
+  const float* pending_mult = nullptr;  // per-output-channel multiplier for the NEXT conv() (NAFBlock beta / gamma)
   bool stem_padded = false;  // X0 lives in the zero-bordered [B][Hp+6][Wp+8][8] layout of the tcgen05 stem
 
   T* alloc(long long elems) {
@@ -355,6 +435,8 @@ struct Builder {
     Epilogue ep;
     memset(&ep, 0, sizeof ep);
     ep.bias = bias ? fw(bias) : nullptr;
+    ep.mult_vec = pending_mult;
+    pending_mult = nullptr;
     ep.silu = silu;
     ep.ss_S = ctx->S;
     bool use_ss = !ss_block.empty();
@@ -539,6 +621,174 @@ struct Builder {
     release(hid);
   }
 
+  // ---- ConditionalNAFNet (DenoisingNAFNet_arch.py:87-188) -------------------------------------------------
+  float* naf_partial = nullptr;
+  float* naf_sca = nullptr;
+
+  void ln_mod(const std::string& gname, const std::string& blk, int off_scale, int off_shift, V in, V out, int H, int W) {
+    int C = in.C, B = plan->B;
+    long long npix = (long long)B * H * W;
+    float* g = fw(gname);
+    int base = ctx->ss_off[blk], S = ctx->S, ppi = H * W;
+    irsde_ctx* c = ctx;
+    plan->ops.push_back(OpRec{CAT_LN, 0.0, [=](Plan* p, cudaStream_t st) {
+      LnMod m;
+      m.ss = p->cur.ss; m.t_ptr = p->cur.t_ptr; m.S = S; m.off_scale = base + off_scale; m.off_shift = base + off_shift;
+      m.img_stride = p->cur.ss_img_stride; m.pix_per_img = ppi;
+      launch_layernorm<T>(in.p, in.pitch, g, nullptr, 0, out.p, out.pitch, npix, C, st, &m);
+      c->launches++;
+    }});
+    plan->ops.back().label = gname + " (LN+mod)";
+    plan->ops.back().bytes = 2.0 * npix * C * sizeof(T);
+  }
+
+  void nafblock(const std::string& pre, V x, V out, int H, int W) {
+    const int c = x.C, B = plan->B, N = H * W;
+    const long long npix = (long long)B * N;
+    irsde_ctx* cx = ctx;
+    T* t1 = tmp(npix * c);
+    ln_mod(pre + "norm1.g", pre, c, 0, x, V{t1, c, c}, H, W);            // x * (scale_att + 1) + shift_att
+    T* t2 = tmp(npix * 2 * c);
+    std::string b1 = pre + "conv1.bias";
+    conv(pre + "conv1.weight", V{t1, c, c}, H, W, 1, 1, 0, 1, b1.c_str(), "", 0, nullptr, V{t2, 2 * c, 2 * c}, 2 * c);
+    release(t1);
+    T* g = tmp(npix * c);
+    {
+      float* w2 = fw(pre + "conv2.weight"); float* bb2 = fw(pre + "conv2.bias");
+      float* ws = fw(pre + "sca.1.weight"); float* bs = fw(pre + "sca.1.bias");
+      float* partial = naf_partial; float* sca = naf_sca;
+      const int nch = dwgate_chunks(H, W);
+      plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
+        launch_dwgate<T>(t2, 2 * c, w2, bb2, g, c, partial, B, H, W, c, st);
+        launch_sca(partial, ws, bs, sca, B, c, nch, N, st);
+        launch_scale_channels<T>(g, c, sca, B, N, c, st);
+        cx->launches += 3;
+      }});
+      plan->ops.back().label = pre + "dw3x3+gate+sca";
+      plan->ops.back().bytes = (double)npix * (2 * c + c + 2 * c) * sizeof(T);
+    }
+    release(t2);
+    T* y = tmp(npix * c);
+    std::string b3 = pre + "conv3.bias";
+    pending_mult = fw(pre + "beta");
+    conv(pre + "conv3.weight", V{g, c, c}, H, W, 1, 1, 0, 1, b3.c_str(), "", 0, &x, V{y, c, c}, c);     // y = inp + conv3(.)*beta
+    release(g);
+    t1 = tmp(npix * c);
+    ln_mod(pre + "norm2.g", pre, 3 * c, 2 * c, V{y, c, c}, V{t1, c, c}, H, W);                          // * (scale_ffn+1) + shift_ffn
+    t2 = tmp(npix * 2 * c);
+    std::string b4 = pre + "conv4.bias";
+    conv(pre + "conv4.weight", V{t1, c, c}, H, W, 1, 1, 0, 1, b4.c_str(), "", 0, nullptr, V{t2, 2 * c, 2 * c}, 2 * c);
+    release(t1);
+    g = tmp(npix * c);
+    plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
+      launch_simple_gate<T>(t2, 2 * c, g, c, npix, c, st);
+      cx->launches++;
+    }});
+    plan->ops.back().label = pre + "simple_gate";
+    release(t2);
+    std::string b5 = pre + "conv5.bias";
+    pending_mult = fw(pre + "gamma");
+    V vy{y, c, c};
+    conv(pre + "conv5.weight", V{g, c, c}, H, W, 1, 1, 0, 1, b5.c_str(), "", 0, &vy, out, c);           // out = y + conv5(.)*gamma
+    release(g);
+    release(y);
+  }
+
+  void build_naf() {
+    const NafCfg& n = ctx->naf;
+    const int B = plan->B, w = n.width, ic = n.img_channel;
+    const int s = 1 << n.n_enc;
+    plan->Hp = plan->H + (s - plan->H % s) % s;
+    plan->Wp = plan->W + (s - plan->W % s) % s;
+    std::vector<int> hs(n.n_enc + 1), ws(n.n_enc + 1);
+    hs[0] = plan->Hp; ws[0] = plan->Wp;
+    for (int i = 1; i <= n.n_enc; ++i) { hs[i] = hs[i - 1] / 2; ws[i] = ws[i - 1] / 2; }
+    size_t pmax = 0, cmax = 0;
+    for (int i = 0; i <= n.n_enc; ++i) {
+      size_t cc = (size_t)w << i;
+      pmax = std::max(pmax, (size_t)B * dwgate_chunks(hs[i], ws[i]) * cc);
+      cmax = std::max(cmax, cc);
+    }
+    naf_partial = (float*)dev_alloc(ctx, pmax * sizeof(float), &plan->allocs);
+    naf_sca = (float*)dev_alloc(ctx, (size_t)B * cmax * sizeof(float), &plan->allocs);
+    if (!naf_partial || !naf_sca) { ok = false; err = "cudaMalloc failed"; return; }
+    const int C0 = 2 * ic, pitch0 = (C0 + 7) / 8 * 8;
+    const long long np0 = (long long)B * hs[0] * ws[0];
+    T* X0 = alloc(np0 * pitch0);
+    int Hh = plan->H, Ww = plan->W, Hp = plan->Hp, Wp = plan->Wp;
+    irsde_ctx* cx = ctx;
+    plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan* p, cudaStream_t st) {
+      launch_prep_input<T>(p->cur.x, p->cur.mu, X0, B, ic, Hh, Ww, Hp, Wp, pitch0, 1, st, 0, 0, 0, 0, 1);  // zero pad
+      cx->launches++;
+    }});
+    T* xin = alloc(np0 * w);
+    conv("intro.weight", V{X0, pitch0, C0}, hs[0], ws[0], 3, 1, 1, 1, "intro.bias", "", 0, nullptr, V{xin, w, w}, w);
+    V cur{xin, w, w};
+    std::vector<V> encs;
+    char nb[64];
+    for (int i = 0; i < n.n_enc; ++i) {
+      const int c = w << i;
+      const long long npix = (long long)B * hs[i] * ws[i];
+      for (int j = 0; j < n.enc[i]; ++j) {
+        T* o = alloc(npix * c);
+        snprintf(nb, sizeof nb, "encoders.%d.%d.", i, j);
+        nafblock(nb, cur, V{o, c, c}, hs[i], ws[i]);
+        cur = V{o, c, c};
+      }
+      encs.push_back(cur);
+      T* d = alloc((long long)B * hs[i + 1] * ws[i + 1] * 2 * c);
+      snprintf(nb, sizeof nb, "downs.%d.", i);
+      std::string wn = std::string(nb) + "weight", bn = std::string(nb) + "bias";
+      conv(wn, cur, hs[i], ws[i], 2, 2, 0, 1, bn.c_str(), "", 0, nullptr, V{d, 2 * c, 2 * c}, 2 * c);
+      cur = V{d, 2 * c, 2 * c};
+    }
+    {
+      const int c = w << n.n_enc;
+      const long long npix = (long long)B * hs[n.n_enc] * ws[n.n_enc];
+      for (int j = 0; j < n.middle; ++j) {
+        T* o = alloc(npix * c);
+        snprintf(nb, sizeof nb, "middle_blks.%d.", j);
+        nafblock(nb, cur, V{o, c, c}, hs[n.n_enc], ws[n.n_enc]);
+        cur = V{o, c, c};
+      }
+    }
+    for (int i = 0; i < n.n_dec; ++i) {
+      const int l = n.n_enc - 1 - i;           // level after upsampling
+      const int chan = w << (l + 1), q = chan / 2;
+      const int hl = hs[l + 1], wl = ws[l + 1];
+      const long long np_lo = (long long)B * hl * wl, np_hi = (long long)B * hs[l] * ws[l];
+      T* u = tmp(np_lo * 2 * chan);
+      snprintf(nb, sizeof nb, "ups.%d.0.weight", i);
+      conv(nb, cur, hl, wl, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{u, 2 * chan, 2 * chan}, 2 * chan);
+      T* v = alloc(np_hi * q);
+      V skip = encs[l];
+      plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
+        launch_pixel_shuffle_add<T>(u, 2 * chan, skip.p, skip.pitch, v, q, B, hl, wl, q, st);
+        cx->launches++;
+      }});
+      plan->ops.back().label = std::string(nb) + " pixel_shuffle+skip";
+      release(u);
+      cur = V{v, q, q};
+      for (int j = 0; j < n.dec[i]; ++j) {
+        T* o = alloc(np_hi * q);
+        snprintf(nb, sizeof nb, "decoders.%d.%d.", i, j);
+        nafblock(nb, cur, V{o, q, q}, hs[l], ws[l]);
+        cur = V{o, q, q};
+      }
+    }
+    if (n.latent) {  // latent variant: ending(x + encs[0]) with encs[0] = intro output
+      T* e = alloc(np0 * w);
+      V a = cur;
+      plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
+        launch_add<T>(a.p, a.pitch, xin, w, e, w, np0, w, st);
+        cx->launches++;
+      }});
+      cur = V{e, w, w};
+    }
+    float* dummy = nullptr;
+    conv("ending.weight", cur, hs[0], ws[0], 3, 1, 1, 1, "ending.bias", "", 0, nullptr, V{nullptr, 0, 0}, ic, &dummy);
+  }
+
   void build() {
     const irsde_config& c = ctx->cfg;
     int B = plan->B, nf = c.nf, depth = c.depth;
@@ -645,18 +895,19 @@ int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
   if (B <= 0 || H <= 0 || W <= 0) return fail(ctx, IRSDE_ERR_INVALID, "bad image shape");
   int s = 1 << ctx->cfg.depth;
   // reflect pad needs pad < size (F.pad 'reflect' raises otherwise, DenoisingUNet_arch.py:82)
-  if ((s - H % s) % s >= H || (s - W % s) % s >= W) return fail(ctx, IRSDE_ERR_INVALID, "image too small for reflect padding");
+  if (!ctx->naf.on && ((s - H % s) % s >= H || (s - W % s) % s >= W))
+    return fail(ctx, IRSDE_ERR_INVALID, "image too small for reflect padding");
   Plan* p = new Plan();
   p->B = B; p->H = H; p->W = W;
   std::string err;
   bool ok;
   if (ctx->cfg.precision == IRSDE_PREC_FP32) {
     Builder<float> b{ctx, p};
-    b.build();
+    if (ctx->naf.on) b.build_naf(); else b.build();
     ok = b.ok; err = b.err;
   } else {
     Builder<bf16> b{ctx, p};
-    b.build();
+    if (ctx->naf.on) b.build_naf(); else b.build();
     ok = b.ok; err = b.err;
   }
   long long n = (long long)B * ctx->cfg.in_nc * H * W;
@@ -749,6 +1000,20 @@ int upload_coeffs(irsde_ctx* ctx, int mode, const float* tab, int T) {
   return IRSDE_OK;
 }
 
+// times[rows] -> table[rows][S] for either network family
+void time_rows(irsde_ctx* ctx, const float* times, int rows, float* temb_ws, float* table, cudaStream_t st) {
+  if (ctx->naf.on) {
+    launch_naf_time_gate(times, rows, ctx->naf.width, ctx->raw["time_mlp.1.weight"].dev, ctx->raw["time_mlp.1.bias"].dev,
+                         ctx->raw["time_mlp.3.weight"].dev, ctx->raw["time_mlp.3.bias"].dev, temb_ws, st);
+    launch_time_rows(temb_ws, rows, 2 * ctx->naf.width, ctx->wall, ctx->ball, ctx->S, table, st);
+  } else {
+    launch_time_table(times, rows, ctx->cfg.nf, ctx->raw["time_mlp.1.weight"].dev, ctx->raw["time_mlp.1.bias"].dev,
+                      ctx->raw["time_mlp.3.weight"].dev, ctx->raw["time_mlp.3.bias"].dev, ctx->wall, ctx->ball, ctx->S, temb_ws,
+                      table, st);
+  }
+  ctx->launches += 2;
+}
+
 int ensure_chain_table(irsde_ctx* ctx, Plan* p, int T, cudaStream_t st) {
   int rows = T + 1;
   if (rows > p->chain_cap) {
@@ -765,10 +1030,7 @@ int ensure_chain_table(irsde_ctx* ctx, Plan* p, int T, cudaStream_t st) {
     for (int m = 0; m < IRSDE_NUM_MODES; ++m)
       if (p->graph[m]) { cudaGraphExecDestroy(p->graph[m]); p->graph[m] = nullptr; }
   }
-  launch_time_table(p->chain_times, rows, ctx->cfg.nf, ctx->raw["time_mlp.1.weight"].dev, ctx->raw["time_mlp.1.bias"].dev,
-                    ctx->raw["time_mlp.3.weight"].dev, ctx->raw["time_mlp.3.bias"].dev, ctx->wall, ctx->ball, ctx->S,
-                    p->chain_temb, p->chain_table, st);
-  ctx->launches += 2;
+  time_rows(ctx, p->chain_times, rows, p->chain_temb, p->chain_table, st);
   return IRSDE_OK;
 }
 
@@ -812,6 +1074,34 @@ int irsde_create(const irsde_config* cfg, irsde_ctx** out) {
   return IRSDE_OK;
 }
 
+int irsde_create_nafnet(const irsde_nafnet_config* ncfg, irsde_ctx** out) {
+  if (!ncfg || !out) return fail(nullptr, IRSDE_ERR_INVALID, "null argument");
+  if (ncfg->width < 4 || ncfg->width % 2 || ncfg->img_channel < 1 || ncfg->n_levels < 0 || ncfg->n_levels > 8 ||
+      ncfg->middle_blk_num < 0)
+    return fail(nullptr, IRSDE_ERR_INVALID, "bad NAFNet configuration");
+  irsde_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.in_nc = cfg.out_nc = ncfg->img_channel;
+  cfg.nf = ncfg->width;
+  cfg.depth = ncfg->n_levels > 0 ? ncfg->n_levels : 1;
+  cfg.variant = IRSDE_NET_CONDITIONAL;
+  cfg.precision = ncfg->precision;
+  cfg.device = ncfg->device;
+  cfg.reserved = ncfg->reserved;
+  int rc = irsde_create(&cfg, out);
+  if (rc) return rc;
+  irsde_ctx* c = *out;
+  c->cfg.depth = ncfg->n_levels;
+  c->naf.on = true;
+  c->naf.img_channel = ncfg->img_channel;
+  c->naf.width = ncfg->width;
+  c->naf.middle = ncfg->middle_blk_num;
+  c->naf.n_enc = c->naf.n_dec = ncfg->n_levels;
+  for (int i = 0; i < ncfg->n_levels; ++i) { c->naf.enc[i] = ncfg->enc_blk_nums[i]; c->naf.dec[i] = ncfg->dec_blk_nums[i]; }
+  c->naf.latent = ncfg->latent != 0;
+  return IRSDE_OK;
+}
+
 void irsde_destroy(irsde_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
@@ -850,7 +1140,7 @@ int irsde_load_tensor(irsde_ctx* ctx, const char* name, const void* data, int32_
 int irsde_finalize_weights(irsde_ctx* ctx) {
   if (!ctx) return fail(nullptr, IRSDE_ERR_INVALID, "null ctx");
   cudaSetDevice(ctx->cfg.device);
-  auto specs = param_specs(ctx->cfg);
+  auto specs = ctx->naf.on ? naf_param_specs(ctx->naf) : param_specs(ctx->cfg);
   for (auto& s : specs) {
     auto it = ctx->raw.find(s.name);
     if (it == ctx->raw.end()) return fail(ctx, IRSDE_ERR_STATE, "missing state-dict entry " + s.name);
@@ -861,6 +1151,9 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
   for (auto& s : specs) {
     if (s.shape.size() != 4) continue;  // vectors / Linear matrices stay fp32 as loaded
     if (s.name.size() > 2 && s.name.substr(s.name.size() - 2) == ".g") continue;
+    if (ctx->naf.on && (s.shape[0] == 1 || s.name.find("conv2.weight") != std::string::npos ||
+                        s.name.find("sca.1.weight") != std::string::npos))
+      continue;  // beta/gamma vectors, depthwise and SCA weights are consumed raw
     int Cout = (int)s.shape[0], Cin = (int)s.shape[1], KH = (int)s.shape[2], KW = (int)s.shape[3];
     long long n = (long long)Cout * Cin * KH * KW;
     float*& ws = ctx->w_simt[s.name];
@@ -885,21 +1178,31 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
         pack_tc_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cin, KH, KW);
     }
   }
-  // time-modulation: concatenate every ResBlock's mlp.1 into one [S][4nf] matrix
-  auto rbs = resblocks(ctx->cfg);
-  int td = ctx->cfg.nf * 4, S = 0;
-  for (auto& rb : rbs) { ctx->ss_off[rb.pre] = S; S += 2 * rb.cout; }
+  // time-modulation: concatenate every block's mlp.1 into one [S][td_in] matrix
+  // (UNet ResBlock: Linear(4nf -> 2*Cout); NAFBlock: Linear(2w -> 4c))
+  struct TB { std::string pre; int rows; };
+  std::vector<TB> tbs;
+  int td = 0;
+  if (ctx->naf.on) {
+    td = 2 * ctx->naf.width;
+    for (auto& b : naf_blocks(ctx->naf)) tbs.push_back({b.pre, 4 * b.c});
+  } else {
+    td = ctx->cfg.nf * 4;
+    for (auto& rb : resblocks(ctx->cfg)) tbs.push_back({rb.pre, 2 * rb.cout});
+  }
+  int S = 0;
+  for (auto& t : tbs) { ctx->ss_off[t.pre] = S; S += t.rows; }
   if (!ctx->wall) {
     ctx->wall = (float*)dev_alloc(ctx, (size_t)S * td * 4, &ctx->allocs);
     ctx->ball = (float*)dev_alloc(ctx, (size_t)S * 4, &ctx->allocs);
     if (!ctx->wall || !ctx->ball) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
   }
   ctx->S = S;
-  for (auto& rb : rbs) {
-    int off = ctx->ss_off[rb.pre];
-    CUDA_TRY(ctx, cudaMemcpy(ctx->wall + (size_t)off * td, ctx->raw[rb.pre + "mlp.1.weight"].dev, (size_t)2 * rb.cout * td * 4,
+  for (auto& t : tbs) {
+    int off = ctx->ss_off[t.pre];
+    CUDA_TRY(ctx, cudaMemcpy(ctx->wall + (size_t)off * td, ctx->raw[t.pre + "mlp.1.weight"].dev, (size_t)t.rows * td * 4,
                              cudaMemcpyDeviceToDevice));
-    CUDA_TRY(ctx, cudaMemcpy(ctx->ball + off, ctx->raw[rb.pre + "mlp.1.bias"].dev, (size_t)2 * rb.cout * 4, cudaMemcpyDeviceToDevice));
+    CUDA_TRY(ctx, cudaMemcpy(ctx->ball + off, ctx->raw[t.pre + "mlp.1.bias"].dev, (size_t)t.rows * 4, cudaMemcpyDeviceToDevice));
   }
   CUDA_TRY(ctx, cudaDeviceSynchronize());
   ctx->finalized = true;
@@ -944,10 +1247,7 @@ int irsde_noise_fn(irsde_ctx* ctx, const float* x, const float* mu, const float*
   int rc = build_plan(ctx, B, H, W, &p);
   if (rc) return rc;
   CUDA_TRY(ctx, cudaMemcpyAsync(p->fwd_times, times, (size_t)n_times * 4, cudaMemcpyHostToDevice, st));
-  launch_time_table(p->fwd_times, n_times, ctx->cfg.nf, ctx->raw["time_mlp.1.weight"].dev, ctx->raw["time_mlp.1.bias"].dev,
-                    ctx->raw["time_mlp.3.weight"].dev, ctx->raw["time_mlp.3.bias"].dev, ctx->wall, ctx->ball, ctx->S,
-                    p->fwd_temb, p->fwd_table, st);
-  ctx->launches += 2;
+  time_rows(ctx, p->fwd_times, n_times, p->fwd_temb, p->fwd_table, st);
   p->cur.x = x; p->cur.mu = mu; p->cur.out = out;
   p->cur.ss = p->fwd_table; p->cur.t_ptr = p->d_zero; p->cur.ss_img_stride = (n_times > 1) ? 1 : 0;
   run_forward(ctx, p, st);

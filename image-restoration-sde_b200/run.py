@@ -90,6 +90,10 @@ def install(script_dir):
         if len(params) == 3:  # (self, x, time): denoising-sde variant
             ours = irsde_b200.DenoisingUNet
     mods.ConditionalUNet = ours
+    if hasattr(mods, "ConditionalNAFNet"):
+        latent = "latent" in os.path.basename(os.path.abspath(script_dir))
+        import functools
+        mods.ConditionalNAFNet = functools.partial(irsde_b200.ConditionalNAFNet, latent=latent) if latent else irsde_b200.ConditionalNAFNet
     return utils, mods
 
 

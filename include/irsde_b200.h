@@ -62,9 +62,28 @@ typedef struct {
   int32_t reserved;
 } irsde_config;
 
+/* Refusion score network: ConditionalNAFNet(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums)
+ * (codes/config/deraining/models/modules/DenoisingNAFNet_arch.py:87-143); latent != 0 selects the latent
+ * variant whose last conv sees x + intro(x) (codes/config/latent-dehazing/models/modules/DenoisingNAFNet_arch.py:176). */
+typedef struct {
+  int32_t img_channel;
+  int32_t width;
+  int32_t middle_blk_num;
+  int32_t n_levels;          /* len(enc_blk_nums) == len(dec_blk_nums), <= 8 */
+  int32_t enc_blk_nums[8];
+  int32_t dec_blk_nums[8];
+  int32_t latent;
+  int32_t precision;         /* IRSDE_PREC_* */
+  int32_t device;
+  int32_t reserved;
+} irsde_nafnet_config;
+
 /* Replaces `ConditionalUNet(in_nc,out_nc,nf,depth)` + `.to(device)`
  * (DenoisingUNet_arch.py:20, models/denoising_model.py:36). */
 int irsde_create(const irsde_config* cfg, irsde_ctx** out);
+/* Same context type, ConditionalNAFNet architecture; every other entry point (load_tensor, noise_fn, reverse, ...)
+ * is shared.  Replaces `ConditionalNAFNet(...)` + `.to(device)` (DenoisingNAFNet_arch.py:89). */
+int irsde_create_nafnet(const irsde_nafnet_config* cfg, irsde_ctx** out);
 void irsde_destroy(irsde_ctx* ctx);
 const char* irsde_last_error(const irsde_ctx* ctx);
 /* "irsde_b200 <version> sm_100a" */

@@ -370,3 +370,152 @@ def make_weights(in_nc, out_nc, nf, depth, variant="conditional", seed=0, out_ga
             P[name] = (torch.rand(shp, generator=g) * 2 - 1) * bound
     P["final_conv.weight"] *= out_gain
     return P
+
+
+# --------------------------------------------------------------------------------------
+# score network #2: ConditionalNAFNet (Refusion)  codes/config/deraining/models/modules/DenoisingNAFNet_arch.py
+# --------------------------------------------------------------------------------------
+
+
+def _gate(x, dim=1):
+    """SimpleGate: DenoisingNAFNet_arch.py:9-12."""
+    a, b = x.chunk(2, dim=dim)
+    return a * b
+
+
+def naf_block(P, pre, x, t):
+    """NAFBlock.forward: DenoisingNAFNet_arch.py:51-84 (time chunk order: shift_att, scale_att, shift_ffn, scale_ffn)."""
+    te = F.linear(_gate(t, dim=-1), P[pre + "mlp.1.weight"], P[pre + "mlp.1.bias"])[:, :, None, None]
+    shift_att, scale_att, shift_ffn, scale_ffn = te.chunk(4, dim=1)
+    inp = x
+    x = layer_norm_c(x, P[pre + "norm1.g"])
+    x = x * (scale_att + 1) + shift_att
+    x = F.conv2d(x, P[pre + "conv1.weight"], P[pre + "conv1.bias"])
+    x = F.conv2d(x, P[pre + "conv2.weight"], P[pre + "conv2.bias"], padding=1, groups=x.shape[1])
+    x = _gate(x)
+    pooled = x.mean(dim=(2, 3), keepdim=True)
+    x = x * F.conv2d(pooled, P[pre + "sca.1.weight"], P[pre + "sca.1.bias"])
+    x = F.conv2d(x, P[pre + "conv3.weight"], P[pre + "conv3.bias"])
+    y = inp + x * P[pre + "beta"]
+    x = layer_norm_c(y, P[pre + "norm2.g"])
+    x = x * (scale_ffn + 1) + shift_ffn
+    x = F.conv2d(x, P[pre + "conv4.weight"], P[pre + "conv4.bias"])
+    x = _gate(x)
+    x = F.conv2d(x, P[pre + "conv5.weight"], P[pre + "conv5.bias"])
+    return y + x * P[pre + "gamma"]
+
+
+def nafnet_forward(P, inp, cond, time, width, enc_blk_nums, middle_blk_num, dec_blk_nums, latent=False):
+    """ConditionalNAFNet.forward: DenoisingNAFNet_arch.py:147-188; latent variant
+    (codes/config/latent-dehazing/models/modules/DenoisingNAFNet_arch.py:147-181): ending(x + encs[0])."""
+    if isinstance(time, (int, float)):
+        time = torch.tensor([time])
+    time = time.reshape(-1)
+    x = torch.cat([inp - cond, cond], dim=1)
+    half = width // 2
+    freqs = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1)))
+    emb = time[:, None] * freqs[None, :]
+    emb = torch.cat((emb.sin(), emb.cos()), dim=-1)
+    t = F.linear(emb, P["time_mlp.1.weight"], P["time_mlp.1.bias"])
+    t = F.linear(_gate(t, dim=-1), P["time_mlp.3.weight"], P["time_mlp.3.bias"])
+    H, W = x.shape[2:]
+    s = 2 ** len(enc_blk_nums)
+    x = F.pad(x, (0, (s - W % s) % s, 0, (s - H % s) % s))  # zero pad (not reflect)
+    x = F.conv2d(x, P["intro.weight"], P["intro.bias"], padding=1)
+    x_intro = x
+    encs = []
+    for i, num in enumerate(enc_blk_nums):
+        for j in range(num):
+            x = naf_block(P, "encoders.%d.%d." % (i, j), x, t)
+        encs.append(x)
+        x = F.conv2d(x, P["downs.%d.weight" % i], P["downs.%d.bias" % i], stride=2)
+    for j in range(middle_blk_num):
+        x = naf_block(P, "middle_blks.%d." % j, x, t)
+    for i, num in enumerate(dec_blk_nums):
+        x = F.pixel_shuffle(F.conv2d(x, P["ups.%d.0.weight" % i]), 2)
+        x = x + encs[len(encs) - 1 - i]
+        for j in range(num):
+            x = naf_block(P, "decoders.%d.%d." % (i, j), x, t)
+    if latent:
+        x = x + x_intro
+    x = F.conv2d(x, P["ending.weight"], P["ending.bias"], padding=1)
+    return x[..., :H, :W]
+
+
+def nafnet_param_shapes(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums):
+    """State-dict names -> shapes in the reference's registration order (DenoisingNAFNet_arch.py:15-49,89-143)."""
+    S = {}
+    td = width * 4
+    S["time_mlp.1.weight"] = (td * 2, width)
+    S["time_mlp.1.bias"] = (td * 2,)
+    S["time_mlp.3.weight"] = (td, td)
+    S["time_mlp.3.bias"] = (td,)
+    S["intro.weight"] = (width, img_channel * 2, 3, 3)
+    S["intro.bias"] = (width,)
+    S["ending.weight"] = (img_channel, width, 3, 3)
+    S["ending.bias"] = (img_channel,)
+
+    def blk(pre, c):
+        S[pre + "beta"] = (1, c, 1, 1)
+        S[pre + "gamma"] = (1, c, 1, 1)
+        S[pre + "mlp.1.weight"] = (4 * c, td // 2)
+        S[pre + "mlp.1.bias"] = (4 * c,)
+        S[pre + "conv1.weight"] = (2 * c, c, 1, 1)
+        S[pre + "conv1.bias"] = (2 * c,)
+        S[pre + "conv2.weight"] = (2 * c, 1, 3, 3)
+        S[pre + "conv2.bias"] = (2 * c,)
+        S[pre + "conv3.weight"] = (c, c, 1, 1)
+        S[pre + "conv3.bias"] = (c,)
+        S[pre + "sca.1.weight"] = (c, c, 1, 1)
+        S[pre + "sca.1.bias"] = (c,)
+        S[pre + "conv4.weight"] = (2 * c, c, 1, 1)
+        S[pre + "conv4.bias"] = (2 * c,)
+        S[pre + "conv5.weight"] = (c, c, 1, 1)
+        S[pre + "conv5.bias"] = (c,)
+        S[pre + "norm1.g"] = (1, c, 1, 1)
+        S[pre + "norm2.g"] = (1, c, 1, 1)
+
+    chan = width
+    enc_c = []
+    for i, num in enumerate(enc_blk_nums):
+        for j in range(num):
+            blk("encoders.%d.%d." % (i, j), chan)
+        enc_c.append(chan)
+        chan *= 2
+    mid_c = chan
+    dec_c = []
+    for i, num in enumerate(dec_blk_nums):
+        chan //= 2
+        for j in range(num):
+            blk("decoders.%d.%d." % (i, j), chan)
+        dec_c.append(chan)
+    for j in range(middle_blk_num):
+        blk("middle_blks.%d." % j, mid_c)
+    chan = mid_c
+    for i in range(len(dec_blk_nums)):
+        S["ups.%d.0.weight" % i] = (chan * 2, chan, 1, 1)
+        chan //= 2
+    chan = width
+    for i in range(len(enc_blk_nums)):
+        S["downs.%d.weight" % i] = (chan * 2, chan, 2, 2)
+        S["downs.%d.bias" % i] = (chan * 2,)
+        chan *= 2
+    return S
+
+
+def make_nafnet_weights(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    for name, shp in nafnet_param_shapes(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums).items():
+        if name.endswith(".g"):
+            P[name] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith("beta") or name.endswith("gamma"):
+            P[name] = 0.5 * torch.randn(shp, generator=g)  # reference inits these to zero (identity blocks)
+        elif name.endswith("bias"):
+            P[name] = 0.05 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            P[name] = (torch.rand(shp, generator=g) * 2 - 1) * math.sqrt(3.0 / fan_in)
+    return P

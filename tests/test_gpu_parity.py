@@ -310,3 +310,57 @@ def test_step_bf16_teacher_forced(lib, golden):
         ref = O.irsde_sde_step(sc, xt, lq, eps_o, z, t)
         out = sde._native_step(lib._lib.MODE_SDE, xt.to(dev), sde.mu, sde.noise_fn(xt.to(dev), t), z.to(dev), t)
         assert _maxdiff(out, ref) < 1e-3, (t, _maxdiff(out, ref))
+
+
+# ------------------------------------------------------------------------------------------------
+# ConditionalNAFNet (Refusion score network)
+# ------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def golden_naf():
+    import os
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_nafnet.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("key", ["nafnet", "nafnet_latent"])
+def test_nafnet_forward_fp32(lib, golden_naf, key):
+    """fp32 parity mode vs the reference's own output (zero pad 18x23 -> 20x24, scalar and per-image t)."""
+    dev = _dev()
+    g = golden_naf[key]
+    c = g["cfg"]
+    net = lib.ConditionalNAFNet(latent=g["latent"], precision="fp32", **c)
+    assert list(net.state_dict().keys()) == list(g["state"].keys())
+    net.load_state_dict(g["state"], strict=True)
+    net = net.to(dev)
+    y = net(g["x"].to(dev), g["cond"].to(dev), g["t_int"])
+    assert _maxdiff(y, g["y"]) < 1e-4
+    yv = net(g["x"].to(dev), g["cond"].to(dev), g["t_vec"])
+    assert _maxdiff(yv, g["y_vec"]) < 1e-4
+
+
+def test_nafnet_chain_fp32_and_bf16(lib):
+    """Refusion-style chain (reverse_sde through NAFNet) vs the oracle: fp32 <= 1e-3; bf16 forward <= 4% of scale."""
+    dev = _dev()
+    cfg = dict(img_channel=4, width=16, middle_blk_num=1, enc_blk_nums=[1, 1], dec_blk_nums=[1, 1])
+    P = O.make_nafnet_weights(4, 16, 1, [1, 1], [1, 1], seed=3)
+    g = torch.Generator().manual_seed(8)
+    lq = torch.rand(2, 4, 24, 32, generator=g)
+    T = 6
+    sc = O.Schedule(50, T, "cosine", 0.005)
+    xT = lq + torch.randn(lq.shape, generator=g) * sc.max_sigma
+    zs = torch.randn((T,) + tuple(lq.shape), generator=g)
+    fn = lambda x, t: O.nafnet_forward(P, x, lq, t, 16, [1, 1], 1, [1, 1], latent=True)
+    ref = O.reverse_chain(sc, fn, xT, lq, zs, "sde")
+    net = lib.ConditionalNAFNet(latent=True, precision="fp32", **cfg)
+    net.load_state_dict(P, strict=True)
+    net = net.to(dev)
+    sde = lib.IRSDE(50, T, schedule="cosine", eps=0.005, device=dev)
+    sde.set_model(net)
+    sde.set_mu(lq.to(dev))
+    x0 = sde.reverse_sde(xT.to(dev), zs=zs.to(dev))
+    assert _maxdiff(x0, ref) < 1e-3
+    netb = lib.ConditionalNAFNet(latent=True, precision="bf16", **cfg)
+    netb.load_state_dict(P, strict=True)
+    netb = netb.to(dev)
+    yo = fn(xT, 3)
+    yb = netb(xT.to(dev), lq.to(dev), 3)
+    assert _maxdiff(yb, yo) < 4e-2 * yo.abs().max().item()

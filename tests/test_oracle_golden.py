@@ -95,3 +95,17 @@ def test_dsde_chain(golden):
     assert O.get_optimal_timestep(sc, 25) == g["Tstar"]
     _close(O.reverse_chain(sc, net, g["x"], None, g["zs"], "dsde_sde", T=g["Tstar"]), g["x0_sde"], 2e-4)
     _close(O.reverse_chain(sc, net, g["x"], None, g["zs"], "dsde_ode", T=g["Tstar"]), g["x0_ode"], 2e-4)
+
+
+def test_nafnet_oracle_vs_reference():
+    import os
+    g_all = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_nafnet.pt"), weights_only=False)
+    for key, g in g_all.items():
+        c = g["cfg"]
+        args = (c["width"], c["enc_blk_nums"], c["middle_blk_num"], c["dec_blk_nums"])
+        y = O.nafnet_forward(g["state"], g["x"], g["cond"], g["t_int"], *args, latent=g["latent"])
+        _close(y, g["y"], 1e-5)
+        yv = O.nafnet_forward(g["state"], g["x"], g["cond"], g["t_vec"], *args, latent=g["latent"])
+        _close(yv, g["y_vec"], 1e-5)
+        shapes = O.nafnet_param_shapes(c["img_channel"], c["width"], c["middle_blk_num"], c["enc_blk_nums"], c["dec_blk_nums"])
+        assert list(shapes) == list(g["state"])
