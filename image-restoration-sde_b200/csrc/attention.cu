@@ -206,7 +206,7 @@ static const int LA_MAXBLK = 64;            // partial records per image
 
 static int la_blocks_per_image(int B, int N) {
   int nchunks = (N + LA_PIX - 1) / LA_PIX;
-  int nblk = (444 + B - 1) / B;
+  int nblk = (296 + B - 1) / B;  // 2 resident blocks per SM (smem-limited) => one full wave
   if (nblk > LA_MAXBLK) nblk = LA_MAXBLK;
   if (nblk > nchunks) nblk = nchunks;
   return nblk < 1 ? 1 : nblk;
@@ -311,8 +311,10 @@ __global__ void __launch_bounds__(1024) la_combine_kernel(const float* __restric
   const int d = tid >> 5;
   const float* base = part + (long long)b * LA_MAXBLK * LA_REC + h * 1088;
   float M = -INFINITY;
+#pragma unroll 8
   for (int k = 0; k < nblk; ++k) M = fmaxf(M, base[(long long)k * LA_REC + d]);
   float S = 0.f, acc = 0.f;
+#pragma unroll 8
   for (int k = 0; k < nblk; ++k) {
     const float* rec = base + (long long)k * LA_REC;
     const float w = expf(rec[d] - M);

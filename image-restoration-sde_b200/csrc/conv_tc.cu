@@ -46,6 +46,7 @@ struct TcParams {
   int tma_store;        // persistent kernel: bf16 NHWC output through smem + TMA bulk store
   int qsm;              // LinearAttention q: softmax over each 32-channel head * 32^-0.5 for output channels < 128
   int w_per_image;      // weights tensor is [B][Cout][Cin]: third TMA coordinate = image index
+  int rows_a_bytes;     // ROWS mode: bytes of one A box ((BH+2) x BW x 128)
   unsigned long long* dbg;  // optional [grid][8] cycle counters (IRSDE_TC_DEBUG=1)
   const bf16* res;
   int res_pitch;
@@ -374,18 +375,30 @@ constexpr int PATCH_W = 10, PATCH_H = 18;
 constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;   // 23040
 constexpr int PATCH_STRIDE = 24 * 1024;                // per-buffer stride (1024-aligned)
 
-template <int BN, bool PATCH>
+//
+// ROWS mode (default for 3x3 stride-1 convs with BN <= 128): a stage is ONE TMA box of (BH+2) image rows x BW pixels
+// for a given horizontal shift dw, plus the three weight tiles of the taps (dh=-1,0,1; dw).  The three vertical taps
+// read 1024-byte-ALIGNED row windows of the same box (window dh starts (dh+1)*BW pixel rows in), so the A operand
+// is fetched 3x instead of 9x per 64-channel chunk with ordinary aligned UMMA descriptors, and one full/empty
+// barrier round covers 12 MMAs.
+constexpr int ROWS_A_SLOT = 20 * 1024;  // (8+2) rows x 16 px x 128 B (or 18 x 8 px for narrow images)
+
+template <int BN, int MODE>
 struct TcCfgP {
+  static constexpr bool PATCH = MODE == 1;
+  static constexpr bool ROWS = MODE == 2;
   static constexpr int B_STAGE_BYTES = BN * 128;
   // non-PATCH: G consecutive k-iterations (64-channel chunks) share one full/empty barrier round, which amortises the
   // mbarrier wait + tcgen05.commit of the single MMA-issuing thread over 4*G MMAs (matters for narrow N tiles)
   static constexpr int G = 1;  // measured: G=2 trades issue overhead for coarser prefetch granularity; no net gain
-  static constexpr int STAGES = PATCH ? (BN == 256 ? 4 : (BN == 128 ? 8 : 12)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
-  static constexpr int STAGE_BYTES = PATCH ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;  // per k-iteration
-  static constexpr int A_BYTES = PATCH ? 2 * PATCH_STRIDE : STAGES * G * A_STAGE_BYTES;   // patch double buffer | A ring
+  static constexpr int STAGES = ROWS ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
+                                     : (PATCH ? (BN == 256 ? 4 : (BN == 128 ? 8 : 12)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+  static constexpr int BSUB = ROWS ? 3 : 1;  // weight tiles per stage
+  static constexpr int STAGE_BYTES = PATCH ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;  // per k-iteration (modes 0/1)
+  static constexpr int A_BYTES = ROWS ? STAGES * ROWS_A_SLOT : (PATCH ? 2 * PATCH_STRIDE : STAGES * G * A_STAGE_BYTES);
   static constexpr int EPI_FLOATS = 3 * BN;
   static constexpr int STG_BYTES = 8 * 2048;  // per epilogue warp: one 32 rows x 64 B staging tile for TMA stores
-  static constexpr int SMEM_BYTES = 1024 + A_BYTES + STAGES * G * B_STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 512;
+  static constexpr int SMEM_BYTES = 1024 + A_BYTES + STAGES * G * BSUB * B_STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 512;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
@@ -444,19 +457,21 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
     }                                           \
   } while (0)
 
-template <int BN, bool PATCH>
+template <int BN, int MODE>
 __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                  const __grid_constant__ OutMaps map_o,
                                                                  const __grid_constant__ TcParams P, int tiles_m,
                                                                  int num_tiles) {
-  using Cfg = TcCfgP<BN, PATCH>;
+  using Cfg = TcCfgP<BN, MODE>;
+  constexpr bool PATCH = Cfg::PATCH;
+  constexpr bool ROWS = Cfg::ROWS;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;                       // A ring, or the two halo-patch buffers in PATCH mode
   uint8_t* smem_b = smem + Cfg::A_BYTES;
-  uint8_t* smem_stg = smem_b + STAGES * Cfg::G * Cfg::B_STAGE_BYTES;  // 1024-aligned
+  uint8_t* smem_stg = smem_b + STAGES * Cfg::G * Cfg::BSUB * Cfg::B_STAGE_BYTES;  // 1024-aligned
   float* s_epi = reinterpret_cast<float*>(smem_stg + Cfg::STG_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::EPI_FLOATS);
   uint64_t* full_bar = bars;
@@ -506,7 +521,22 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       long long w_prod = 0, t_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile, tiles_m, BN);
-        if constexpr (PATCH) {
+        if constexpr (ROWS) {
+          for (int kc = 0; kc < P.kchunks; ++kc) {
+            for (int dwi = 0; dwi < 3; ++dwi, ++it) {
+              const int s = it % STAGES;
+              if (it >= STAGES) DBG_WAIT(w_prod, &empty_bar[s], ((it / STAGES) - 1) & 1);
+              if (elect_one()) {
+                mbar_expect_tx(&full_bar[s], P.rows_a_bytes + 3 * Cfg::B_STAGE_BYTES);
+                tma_load_5d(smem_a + s * ROWS_A_SLOT, &map_a, &full_bar[s], kc * 64, t.w0 + dwi - 1, t.h0 - 1, t.b, 0);
+#pragma unroll
+                for (int j = 0; j < 3; ++j)  // taps (dh = j-1, dw = dwi-1): index (dh+1)*3 + (dw+1)
+                  tma_load_3d(smem_b + (s * 3 + j) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0, j * 3 + dwi);
+              }
+              __syncwarp();
+            }
+          }
+        } else if constexpr (PATCH) {
           for (int kc = 0; kc < P.kchunks; ++kc, ++pc) {
             const int pb = pc & 1;
             if (pc >= 2) DBG_WAIT(w_prod, &pempty_bar[pb], ((pc >> 1) - 1) & 1);
@@ -563,7 +593,27 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
         if (lt >= 2) DBG_WAIT(w_tempty, &tempty_bar[acc], ((lt >> 1) - 1) & 1);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        if constexpr (PATCH) {
+        if constexpr (ROWS) {
+          const int nst = 3 * P.kchunks;
+          for (int si = 0; si < nst; ++si, ++it) {
+            const int s = it % STAGES;
+            DBG_WAIT(w_full, &full_bar[s], (it / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint32_t a0 = smem_u32(smem_a + s * ROWS_A_SLOT);
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {  // vertical tap dh = j-1: row window starting j*BW pixel rows into the box
+                const uint64_t adesc = make_sw128_desc(a0 + (uint32_t)(j * P.BW * 128));
+                const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + (s * 3 + j) * Cfg::B_STAGE_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (si > 0 || j > 0 || k > 0) ? 1u : 0u);
+              }
+              umma_commit(&empty_bar[s]);
+            }
+            __syncwarp();
+          }
+        } else if constexpr (PATCH) {
           for (int kc = 0; kc < P.kchunks; ++kc, ++pc) {
             const int pb = pc & 1;
             DBG_WAIT(w_full, &pfull_bar[pb], (pc >> 1) & 1);
@@ -772,6 +822,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 int g_num_sms = 148;
 bool g_persist = true;
 bool g_tma_store = true;
+bool g_rows = true;
 bool g_patch = false;  // opt-in (IRSDE_TC_PATCH=1): measured slower than per-tap boxes, see DESIGN.md
 
 }  // namespace
@@ -784,6 +835,7 @@ struct TcConvDesc {
   dim3 grid;
   int tiles_m, num_tiles;
   bool patch;
+  int mode;  // 0 per-tap boxes, 1 PATCH (halo patch, shifted descriptors), 2 ROWS (row-window reuse)
 };
 
 bool tc_init(std::string* err) {
@@ -800,14 +852,17 @@ bool tc_init(std::string* err) {
   cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<32, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, false>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, true>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, false>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, true>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, false>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, true>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, false>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, true>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 1>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 2>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 1>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 2>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 1>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 2>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 1>::SMEM_BYTES);
   {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);
@@ -816,6 +871,8 @@ bool tc_init(std::string* err) {
     g_persist = !(e && e[0] == '0');
     e = getenv("IRSDE_TC_TMA_STORE");
     g_tma_store = !(e && e[0] == '0');
+    e = getenv("IRSDE_TC_ROWS");
+    g_rows = !(e && e[0] == '0');
     e = getenv("IRSDE_TC_PATCH");
     g_patch = (e && e[0] == '1');
   }
@@ -862,7 +919,15 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   // PATCH mode: plain 3x3 / stride 1 / pad 1 on the persistent kernel
   bool patch = g_persist && g_patch && nphases == 1 && planes == 1 && ntaps == 9;
   for (int i = 0; patch && i < 9; ++i) patch = taps[i].dh == i / 3 - 1 && taps[i].dw == i % 3 - 1 && taps[i].plane == 0;
+  int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
+  if (BN == 256 && Cout % 256 != 0 && Cout % 128 == 0) BN = 128;  // e.g. to_qkv (384): no half-empty N tile
+  bool rows = false;
+  if (!patch && g_persist && g_rows && nphases == 1 && planes == 1 && ntaps == 9 && BN <= 128) {
+    rows = true;
+    for (int i = 0; rows && i < 9; ++i) rows = taps[i].dh == i / 3 - 1 && taps[i].dw == i % 3 - 1 && taps[i].plane == 0;
+  }
   d->patch = patch;
+  d->mode = patch ? 1 : (rows ? 2 : 0);
   // tile shape: BW x BH = 128 pixels, minimise padded work
   long long best = -1;
   for (int bw = 128; bw >= 8; bw >>= 1) {
@@ -871,12 +936,14 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
     if (best < 0 || cost < best) { best = cost; P.BW = bw; P.BH = bh; }
   }
   if (patch) { P.BW = 8; P.BH = 16; }
+  if (rows) {  // (BH+2) x BW box must fit the 20 KB slot: BW <= 16
+    if (Win >= 16) { P.BW = 16; P.BH = 8; } else { P.BW = 8; P.BH = 16; }
+    P.rows_a_bytes = (P.BH + 2) * P.BW * 128;
+  }
   P.logBW = 0;
   while ((1 << P.logBW) < P.BW) P.logBW++;
   P.tilesW = (Win + P.BW - 1) / P.BW;
   P.tilesH = (Hin + P.BH - 1) / P.BH;
-  int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
-  if (BN == 256 && Cout % 256 != 0 && Cout % 128 == 0) BN = 128;  // e.g. to_qkv (384): no half-empty N tile
   d->BN = BN;
   d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
   d->tiles_m = P.tilesW * P.tilesH * B * nphases;
@@ -896,6 +963,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
     }
     cuuint32_t box[5] = {64, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1, 1};
     if (patch) { box[1] = PATCH_W; box[2] = PATCH_H; }
+    if (rows) { box[2] = (cuuint32_t)(P.BH + 2); }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(&d->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in, dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -975,19 +1043,25 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
     d->P.dbg = dbg ? dbg_dev : nullptr;
 #define TC_LAUNCH(BNV, PV) \
   conv_tc_persist_kernel<BNV, PV><<<g, 320, TcCfgP<BNV, PV>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles)
-    if (d->patch) {
+    if (d->mode == 2) {
       switch (d->BN) {
-        case 32: TC_LAUNCH(32, true); break;
-        case 64: TC_LAUNCH(64, true); break;
-        case 128: TC_LAUNCH(128, true); break;
-        default: TC_LAUNCH(256, true); break;
+        case 32: TC_LAUNCH(32, 2); break;
+        case 64: TC_LAUNCH(64, 2); break;
+        default: TC_LAUNCH(128, 2); break;
+      }
+    } else if (d->mode == 1) {
+      switch (d->BN) {
+        case 32: TC_LAUNCH(32, 1); break;
+        case 64: TC_LAUNCH(64, 1); break;
+        case 128: TC_LAUNCH(128, 1); break;
+        default: TC_LAUNCH(256, 1); break;
       }
     } else {
       switch (d->BN) {
-        case 32: TC_LAUNCH(32, false); break;
-        case 64: TC_LAUNCH(64, false); break;
-        case 128: TC_LAUNCH(128, false); break;
-        default: TC_LAUNCH(256, false); break;
+        case 32: TC_LAUNCH(32, 0); break;
+        case 64: TC_LAUNCH(64, 0); break;
+        case 128: TC_LAUNCH(128, 0); break;
+        default: TC_LAUNCH(256, 0); break;
       }
     }
 #undef TC_LAUNCH
@@ -998,7 +1072,7 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
       double a[8] = {0};
       for (unsigned i = 0; i < g; ++i) for (int k = 0; k < 8; ++k) a[k] += (double)h[i * 8 + k] / g;
       fprintf(stderr, "TCDBG BN=%d patch=%d grid=%u tiles=%d ntaps=%d kch=%d | prod wait %.0f / %.0f | mma wait full %.0f tempty %.0f / %.0f | epi wait tfull %.0f / %.0f (tiles/cta %.1f)\n",
-              d->BN, (int)d->patch, g, d->num_tiles, d->P.ntaps, d->P.kchunks, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
+              d->BN, d->mode, g, d->num_tiles, d->P.ntaps, d->P.kchunks, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
     }
     return 1;
   }
