@@ -364,3 +364,45 @@ def test_nafnet_chain_fp32_and_bf16(lib):
     yo = fn(xT, 3)
     yb = netb(xT.to(dev), lq.to(dev), 3)
     assert _maxdiff(yb, yo) < 4e-2 * yo.abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------------
+# BASELINE.json full-size workload (config 2: 8x3x256x256, nf=64 depth=4): size-independent properties
+# ------------------------------------------------------------------------------------------------
+def test_full_size_properties_bf16(lib):
+    """At the benchmark size the oracle is too slow, so check properties that do not need it:
+    (1) graph replay == eager launch, bit for bit; (2) run-to-run determinism; (3) batch-sharded (the multi-GPU
+    partition) == unsharded, bit for bit; (4) finite outputs; (5) with eps-hat from the analytic noise of a known x0
+    the sampler update itself contracts toward x0 (sampler-only chain, no network)."""
+    dev = _dev()
+    torch.manual_seed(0)
+    net = lib.ConditionalUNet(3, 3, 64, depth=4, precision="bf16").to(dev)
+    sde = lib.IRSDE(10, 100, schedule="cosine", eps=0.005, device=dev)
+    sde.set_model(net)
+    g = torch.Generator().manual_seed(1234)
+    lq = torch.rand(8, 3, 256, 256, generator=g).to(dev)
+    xT = lq + torch.randn(8, 3, 256, 256, generator=g).to(dev) * sde.max_sigma
+    T = 3
+    zs = torch.randn(T, 8, 3, 256, 256, generator=g).to(dev)
+    sde.set_mu(lq)
+    sde.use_graph = True
+    a = sde.reverse_sde(xT, T=T, zs=zs)
+    b = sde.reverse_sde(xT, T=T, zs=zs)
+    sde.use_graph = False
+    c = sde.reverse_sde(xT, T=T, zs=zs)
+    assert torch.isfinite(a).all()
+    assert torch.equal(a, b) and torch.equal(a, c)
+    parts = []
+    for r in range(2):
+        lo, hi = lib.shard_range(8, r, 2)
+        sde.set_mu(lq[lo:hi])
+        parts.append(sde.reverse_sde(xT[lo:hi], T=T, zs=zs[:, lo:hi]))
+    assert torch.equal(a, torch.cat(parts))
+    # sampler-only chain with the analytic noise (sde_utils.py:231-232): converges to x0
+    sde.set_mu(lq)
+    x0 = torch.rand(8, 3, 256, 256, generator=g).to(dev)
+    x = sde.mu + (x0 - sde.mu) * torch.exp(-sde.thetas_cumsum[100] * sde.dt) + torch.randn_like(x0) * sde.sigma_bars[100]
+    for t in reversed(range(1, 101)):
+        eps_true = sde.get_real_noise(x, x0, t)
+        x = sde._native_step(lib._lib.MODE_POSTERIOR, x, sde.mu, eps_true, torch.randn_like(x), t)
+    assert _maxdiff(x, x0) < 1e-3

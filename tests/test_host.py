@@ -127,3 +127,23 @@ def test_sharded_gather_gloo_world2():
     for rank, out, w in res:
         assert torch.equal(out, expect)
     assert torch.equal(res[0][2], res[1][2]) and res[0][2].abs().sum() > 0
+
+
+def test_launcher_patches_reference_tree():
+    """Drop-in mechanics: on a checkout of the reference, `run.install` swaps the sampler and
+    network classes the reference scripts resolve by name.  Needs the reference tree (absent on the GPU box)."""
+    ref = "/root/reference/codes/config/deraining"
+    if not os.path.isdir(ref):
+        pytest.skip("reference checkout not available")
+    import subprocess
+    import sys
+    code = (
+        "import sys, os; sys.path.insert(0, %r); import irsde_b200; from irsde_b200 import run; os.chdir(%r); "
+        "u, m = run.install(%r); from models import networks; "
+        "assert u.IRSDE is irsde_b200.IRSDE and u.DenoisingSDE is irsde_b200.DenoisingSDE; "
+        "net = networks.define_G({'network_G': {'which_model_G': 'ConditionalUNet', 'setting': dict(in_nc=3, out_nc=3, nf=8, depth=2)}}); "
+        "assert isinstance(net, irsde_b200.ConditionalUNet); "
+        "naf = networks.define_G({'network_G': {'which_model_G': 'ConditionalNAFNet', 'setting': dict(img_channel=3, width=8, enc_blk_nums=[1], middle_blk_num=1, dec_blk_nums=[1])}}); "
+        "assert isinstance(naf, irsde_b200.ConditionalNAFNet); print('ok')" % (ROOT, ref, ref))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
