@@ -126,7 +126,7 @@ def run_reference(args):
     B, H, W, T, nf, depth, ms, eps = WORKLOADS[wl]
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
-        v, dt, sample = cpu_reference_sample(wl, steps_per_sample=2 if i < args.warmup else 3)
+        v, dt, sample = cpu_reference_sample(wl, steps_per_sample=2 if i < args.warmup else 6)
         if i >= args.warmup:
             vals.append(v); secs.append(dt)
     value = len(vals) / sum(1.0 / v for v in vals)  # harmonic mean = total images / total time
@@ -278,7 +278,7 @@ def run_b200(args):
     # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same workload on host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        v, dt, sample = cpu_reference_sample(wl)
+        v, dt, sample = cpu_reference_sample(wl, steps_per_sample=8)
         cpu = {"value": v, "unit": "images/s", "cores": usable_cores(), "kind": "port", "sample": sample, "seconds": dt}
 
     if rank == 0:
