@@ -7,7 +7,7 @@ import ctypes
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libirsde_b200.so")
+LIB_PATH = os.environ.get("IRSDE_B200_LIB") or os.path.join(HERE, "libirsde_b200.so")  # override: A/B of builds
 
 PREC_FP32, PREC_BF16 = 0, 1
 NET_CONDITIONAL, NET_DENOISING = 0, 1

@@ -206,7 +206,10 @@ static const int LA_MAXBLK = 64;            // partial records per image
 
 static int la_blocks_per_image(int B, int N) {
   int nchunks = (N + LA_PIX - 1) / LA_PIX;
-  int nblk = (296 + B - 1) / B;  // 2 resident blocks per SM (smem-limited) => one full wave
+  // The partition must not depend on the batch size: a batch-sharded run has to reproduce the unsharded one bit for
+  // bit (fp32 summation order).  37 blocks per image = one full wave of 2 resident blocks/SM at 8 images per GPU.
+  (void)B;
+  int nblk = 37;
   if (nblk > LA_MAXBLK) nblk = LA_MAXBLK;
   if (nblk > nchunks) nblk = nchunks;
   return nblk < 1 ? 1 : nblk;
