@@ -9,9 +9,10 @@ from . import _lib
 from .sde import IRSDE, DenoisingSDE
 from .unet import ConditionalUNet, DenoisingUNet, unet_param_shapes
 from .nafnet import ConditionalNAFNet, nafnet_param_shapes
+from .latent import UNet, latent_unet_param_shapes
 from .dist import shard_range, sharded_reverse, broadcast_weights
 
-__all__ = ["IRSDE", "DenoisingSDE", "ConditionalUNet", "DenoisingUNet", "ConditionalNAFNet", "unet_param_shapes",
+__all__ = ["IRSDE", "DenoisingSDE", "ConditionalUNet", "DenoisingUNet", "ConditionalNAFNet", "UNet", "unet_param_shapes", "latent_unet_param_shapes",
            "nafnet_param_shapes", "shard_range",
            "sharded_reverse", "broadcast_weights", "_lib"]
 __version__ = "0.1"

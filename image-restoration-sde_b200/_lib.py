@@ -15,7 +15,8 @@ MODE_SDE, MODE_ODE, MODE_POSTERIOR, MODE_DSDE_SDE, MODE_DSDE_ODE = range(5)
 NUM_COEF = 8
 
 # every symbol include/irsde_b200.h declares
-SYMBOLS = ["irsde_create", "irsde_create_nafnet", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
+SYMBOLS = ["irsde_create", "irsde_create_nafnet", "irsde_create_latent_unet", "irsde_latent_shape", "irsde_latent_encode",
+           "irsde_latent_decode", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
            "irsde_finalize_weights", "irsde_set_schedule", "irsde_set_coeffs", "irsde_noise_fn", "irsde_step",
            "irsde_reverse", "irsde_noise_state", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
            "irsde_profile_end"]

@@ -56,6 +56,8 @@ struct Plan {
   int B, H, W, Hp, Wp;
   std::vector<void*> allocs;
   std::vector<OpRec> ops;
+  std::vector<OpRec> ops_dec;  // latent UNet: decode half (ops = encode half)
+  int lat_h = 0, lat_w = 0;     // latent spatial size
   std::vector<TcConvDesc*> tc_descs;
   RunCfg cur;
   // chain state
@@ -77,9 +79,17 @@ struct NafCfg {
   bool latent = false;
 };
 
+// Refusion latent autoencoder UNet (codes/config/latent-dehazing/models/modules/UNet_arch.py:17-97)
+struct LatCfg {
+  bool on = false;
+  int in_ch = 0, out_ch = 0, ch = 0, depth = 0, embed = 0;
+  int mult[9] = {1, 0, 0, 0, 0, 0, 0, 0, 0};  // [1] + ch_mult
+};
+
 struct irsde_ctx {
   irsde_config cfg;
   NafCfg naf;
+  LatCfg lat;
   mutable std::string err;
   std::map<std::string, RawTensor> raw;
   bool finalized = false;
@@ -364,6 +374,59 @@ std::vector<ParamSpec> param_specs(const irsde_config& c) {
   return v;
 }
 
+std::vector<ParamSpec> lat_param_specs(const LatCfg& L) {
+  std::vector<ParamSpec> v;
+  char b[64];
+  v.push_back({"init_conv.weight", {L.ch, L.in_ch, 3, 3}});
+  auto rb = [&](const std::string& pre, int64_t ci, int64_t co) {
+    v.push_back({pre + "block1.proj.weight", {co, ci, 3, 3}});
+    v.push_back({pre + "block2.proj.weight", {co, co, 3, 3}});
+    if (ci != co) v.push_back({pre + "res_conv.weight", {co, ci, 1, 1}});
+  };
+  auto la = [&](const std::string& pre, int64_t C) {
+    v.push_back({pre + "fn.fn.to_qkv.weight", {384, C, 1, 1}});
+    v.push_back({pre + "fn.fn.to_out.0.weight", {C, 128, 1, 1}});
+    v.push_back({pre + "fn.fn.to_out.0.bias", {C}});
+    v.push_back({pre + "fn.fn.to_out.1.g", {1, C, 1, 1}});
+    v.push_back({pre + "fn.norm.g", {1, C, 1, 1}});
+  };
+  for (int i = 0; i < L.depth; ++i) {
+    int64_t di = (int64_t)L.ch * L.mult[i], dout = (int64_t)L.ch * L.mult[i + 1];
+    snprintf(b, sizeof b, "encoder.%d.", i);
+    std::string pre = b;
+    rb(pre + "0.", di, di);
+    rb(pre + "1.", di, di);
+    if (i == L.depth - 1) la(pre + "2.", di);
+    if (i != L.depth - 1) {
+      v.push_back({pre + "3.weight", {dout, di, 4, 4}});
+      v.push_back({pre + "3.bias", {dout}});
+    } else {
+      v.push_back({pre + "3.weight", {dout, di, 3, 3}});
+    }
+  }
+  for (int j = 0; j < L.depth; ++j) {
+    int i = L.depth - 1 - j;
+    int64_t di = (int64_t)L.ch * L.mult[i], dout = (int64_t)L.ch * L.mult[i + 1];
+    snprintf(b, sizeof b, "decoder.%d.", j);
+    std::string pre = b;
+    rb(pre + "0.", dout + di, dout);
+    rb(pre + "1.", dout + di, dout);
+    if (i == L.depth - 1) la(pre + "2.", dout);
+    if (i != 0) {
+      v.push_back({pre + "3.1.weight", {di, dout, 3, 3}});
+      v.push_back({pre + "3.1.bias", {di}});
+    } else {
+      v.push_back({pre + "3.weight", {di, dout, 3, 3}});
+    }
+  }
+  int64_t mid = (int64_t)L.ch * L.mult[L.depth];
+  v.push_back({"latent_conv.weight", {L.embed, mid, 1, 1}});
+  v.push_back({"post_latent_conv.weight", {mid, L.embed, 1, 1}});
+  v.push_back({"final_conv.weight", {L.out_ch, L.ch, 3, 3}});
+  v.push_back({"final_conv.bias", {L.out_ch}});
+  return v;
+}
+
 // ---- plan builder ----------------------------------------------------------------------------------
 template <typename T>
 struct Builder {
@@ -374,6 +437,7 @@ struct Builder {
   std::multimap<size_t, void*> free_tmp;
   std::map<void*, size_t> tmp_size;
   const float* pending_mult = nullptr;  // per-output-channel multiplier for the NEXT conv() (NAFBlock beta / gamma)
+  int nchw_H = 0, nchw_W = 0;           // crop size of fp32 NCHW outputs (0 = the image size)
   bool stem_padded = false;  // X0 lives in the zero-bordered [B][Hp+6][Wp+8][8] layout of the tcgen05 stem
 
   T* alloc(long long elems) {
@@ -497,7 +561,7 @@ struct Builder {
                                        out.pitch, g.Hout, g.Wout, &terr, tc_flags);
         if (!d) { ok = false; err = "tc_conv_create(" + wname + "): " + terr; return; }
         plan->tc_descs.push_back(d);
-        int cH = plan->H, cW = plan->W;
+        int cH = nchw_H ? nchw_H : plan->H, cW = nchw_W ? nchw_W : plan->W;
         plan->ops.push_back(OpRec{CAT_TC, tc_flops, [=](Plan* p, cudaStream_t st) {
           if (use_ss) tc_conv_set_runtime(d, p->cur.ss, p->cur.t_ptr, p->cur.ss_img_stride);
           if (nchw) tc_conv_set_out_nchw(d, p->cur.out, cH, cW);
@@ -510,7 +574,7 @@ struct Builder {
     if (tc_flags || w_override) { ok = false; err = "fused attention conv needs the tensor-core engine: " + wname; return; }
     const float* w = ctx->w_simt[wname];
     if (!w) { ok = false; err = "unpacked weight " + wname; return; }
-    int H = plan->H, Wd = plan->W;
+    int H = nchw_H ? nchw_H : plan->H, Wd = nchw_W ? nchw_W : plan->W;
     plan->ops.push_back(OpRec{CAT_SIMT, simt_flops, [=](Plan* p, cudaStream_t st) {
       Epilogue e = ep;
       if (use_ss) { e.ss = p->cur.ss; e.t_ptr = p->cur.t_ptr; e.ss_img_stride = p->cur.ss_img_stride; }
@@ -519,11 +583,11 @@ struct Builder {
     }});
   }
 
-  void resblock(const std::string& pre, V in, int Cout, V out, int H, int W) {
+  void resblock(const std::string& pre, V in, int Cout, V out, int H, int W, bool time_mod = true) {
     long long npix = (long long)plan->B * H * W;
     T* h1 = tmp(npix * Cout);
     V vh1{h1, Cout, Cout};
-    conv(pre + "block1.proj.weight", in, H, W, 3, 1, 1, 1, nullptr, pre, 1, nullptr, vh1, Cout);
+    conv(pre + "block1.proj.weight", in, H, W, 3, 1, 1, 1, nullptr, time_mod ? pre : std::string(), 1, nullptr, vh1, Cout);
     V res = in;
     T* r = nullptr;
     if (in.C != Cout) {
@@ -619,6 +683,123 @@ struct Builder {
     }
     release(qkv);
     release(hid);
+  }
+
+  // ---- latent autoencoder UNet.encode / UNet.decode (UNet_arch.py:59-91) --------------------------------------
+  // plan->ops = encode (image -> z, skips stay in the decoder's concat buffers), plan->ops_dec = decode (z -> image).
+  void build_latent() {
+    const LatCfg& L = ctx->lat;
+    const int B = plan->B, depth = L.depth;
+    const int s = 1 << depth;
+    plan->Hp = plan->H + (s - plan->H % s) % s;
+    plan->Wp = plan->W + (s - plan->W % s) % s;
+    std::vector<int> hs(depth), ws(depth);
+    hs[0] = plan->Hp; ws[0] = plan->Wp;
+    for (int i = 1; i < depth; ++i) { hs[i] = hs[i - 1] / 2; ws[i] = ws[i - 1] / 2; }
+    plan->lat_h = hs[depth - 1]; plan->lat_w = ws[depth - 1];
+    float* la_partial = (float*)dev_alloc(ctx, linattn_partial_floats(B, hs[depth - 1] * ws[depth - 1]) * sizeof(float), &plan->allocs);
+    float* la_ctx = (float*)dev_alloc(ctx, (size_t)B * 4096 * sizeof(float), &plan->allocs);
+    if (!la_partial || !la_ctx) { ok = false; err = "cudaMalloc failed"; return; }
+    const int C0 = L.in_ch, pitch0 = (C0 + 7) / 8 * 8;
+    const long long np0 = (long long)B * hs[0] * ws[0];
+    T* X0 = alloc(np0 * pitch0);
+    T* H0 = alloc(np0 * L.ch);  // h[0] = init_conv output, added back before final_conv
+    int in_ch = L.in_ch, Hh = plan->H, Ww = plan->W, Hp = plan->Hp, Wp = plan->Wp;
+    irsde_ctx* cx = ctx;
+    plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan* p, cudaStream_t st) {
+      launch_prep_input<T>(p->cur.x, nullptr, X0, B, in_ch, Hh, Ww, Hp, Wp, pitch0, 0, st);  // reflect pad, no condition
+      cx->launches++;
+    }});
+    conv("init_conv.weight", V{X0, pitch0, C0}, hs[0], ws[0], 3, 1, 1, 1, nullptr, "", 0, nullptr, V{H0, L.ch, L.ch}, L.ch);
+    V cur{H0, L.ch, L.ch};
+    std::vector<T*> U1(depth), U2(depth);
+    char nb[64];
+    for (int i = 0; i < depth; ++i) {
+      const int di = L.ch * L.mult[i], dout = L.ch * L.mult[i + 1], H = hs[i], W = ws[i];
+      const long long npix = (long long)B * H * W;
+      U1[i] = alloc(npix * (dout + di));
+      U2[i] = alloc(npix * (dout + di));
+      snprintf(nb, sizeof nb, "encoder.%d.", i);
+      std::string pre = nb;
+      V s2 = view(U2[i], dout + di, dout, di), s1 = view(U1[i], dout + di, dout, di);
+      resblock(pre + "0.", cur, di, s2, H, W, false);
+      if (i == depth - 1) {
+        T* ta = tmp(npix * di);
+        resblock(pre + "1.", s2, di, V{ta, di, di}, H, W, false);
+        attention(pre + "2.", V{ta, di, di}, s1, H, W, false, la_partial, la_ctx);
+        release(ta);
+        T* xm = alloc(npix * dout);
+        conv(pre + "3.weight", s1, H, W, 3, 1, 1, 1, nullptr, "", 0, nullptr, V{xm, dout, dout}, dout);
+        cur = V{xm, dout, dout};
+      } else {
+        resblock(pre + "1.", s2, di, s1, H, W, false);  // Identity attention: the skip is b2's output
+        T* xn = alloc((long long)B * hs[i + 1] * ws[i + 1] * dout);
+        std::string bn = pre + "3.bias";
+        conv(pre + "3.weight", s1, H, W, 4, 2, 1, 1, bn.c_str(), "", 0, nullptr, V{xn, dout, dout}, dout);
+        cur = V{xn, dout, dout};
+      }
+    }
+    {  // z = latent_conv(x): fp32 NCHW [B, embed, lat_h, lat_w] straight from the epilogue
+      float* dummy = nullptr;
+      nchw_H = plan->lat_h; nchw_W = plan->lat_w;
+      conv("latent_conv.weight", cur, plan->lat_h, plan->lat_w, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{nullptr, 0, 0}, L.embed, &dummy);
+      nchw_H = nchw_W = 0;
+    }
+    // ----- decode half
+    std::vector<OpRec> enc_ops;
+    enc_ops.swap(plan->ops);
+    const int mid = L.ch * L.mult[depth];
+    const long long npl = (long long)B * plan->lat_h * plan->lat_w;
+    const int zp = (L.embed + 7) / 8 * 8;
+    T* Z = alloc(npl * zp);
+    int embed = L.embed, lh = plan->lat_h, lw = plan->lat_w;
+    plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan* p, cudaStream_t st) {
+      launch_nchw_to_nhwc<T>(p->cur.x, Z, B, embed, lh, lw, zp, st);
+      cx->launches++;
+    }});
+    {
+      const int i = depth - 1, di = L.ch * L.mult[i];
+      conv("post_latent_conv.weight", V{Z, zp, L.embed}, lh, lw, 1, 1, 0, 1, nullptr, "", 0, nullptr, view(U1[i], mid + di, 0, mid), mid);
+    }
+    for (int j = 0; j < depth; ++j) {
+      const int i = depth - 1 - j, di = L.ch * L.mult[i], dout = L.ch * L.mult[i + 1], H = hs[i], W = ws[i];
+      const long long npix = (long long)B * H * W;
+      snprintf(nb, sizeof nb, "decoder.%d.", j);
+      std::string pre = nb;
+      resblock(pre + "0.", V{U1[i], dout + di, dout + di}, dout, view(U2[i], dout + di, 0, dout), H, W, false);
+      T* tb = tmp(npix * dout);
+      resblock(pre + "1.", V{U2[i], dout + di, dout + di}, dout, V{tb, dout, dout}, H, W, false);
+      V xo{tb, dout, dout};
+      T* tc = nullptr;
+      if (i == depth - 1) {
+        tc = tmp(npix * dout);
+        attention(pre + "2.", V{tb, dout, dout}, V{tc, dout, dout}, H, W, false, la_partial, la_ctx);
+        xo = V{tc, dout, dout};
+      }
+      if (i != 0) {
+        const int dprev_total = L.ch * L.mult[i] + L.ch * L.mult[i - 1];  // concat width of level i-1: dout_{i-1} + di_{i-1}
+        std::string bn = pre + "3.1.bias";
+        conv(pre + "3.1.weight", xo, H, W, 3, 1, 1, 2, bn.c_str(), "", 0, nullptr, view(U1[i - 1], dprev_total, 0, di), di);
+      } else {
+        T* xf = tmp(np0 * L.ch);
+        conv(pre + "3.weight", xo, H, W, 3, 1, 1, 1, nullptr, "", 0, nullptr, V{xf, L.ch, L.ch}, L.ch);
+        T* xs = tmp(np0 * L.ch);
+        int chn = L.ch;
+        plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
+          launch_add<T>(xf, chn, H0, chn, xs, chn, np0, chn, st);   // x + h[0]
+          cx->launches++;
+        }});
+        float* dummy = nullptr;
+        conv("final_conv.weight", V{xs, L.ch, L.ch}, hs[0], ws[0], 3, 1, 1, 1, "final_conv.bias", "", 0, nullptr, V{nullptr, 0, 0},
+             L.out_ch, &dummy);
+        release(xf);
+        release(xs);
+      }
+      release(tb);
+      if (tc) release(tc);
+    }
+    plan->ops_dec.swap(plan->ops);
+    plan->ops.swap(enc_ops);
   }
 
   // ---- ConditionalNAFNet (DenoisingNAFNet_arch.py:87-188) -------------------------------------------------
@@ -903,11 +1084,11 @@ int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
   bool ok;
   if (ctx->cfg.precision == IRSDE_PREC_FP32) {
     Builder<float> b{ctx, p};
-    if (ctx->naf.on) b.build_naf(); else b.build();
+    if (ctx->lat.on) b.build_latent(); else if (ctx->naf.on) b.build_naf(); else b.build();
     ok = b.ok; err = b.err;
   } else {
     Builder<bf16> b{ctx, p};
-    if (ctx->naf.on) b.build_naf(); else b.build();
+    if (ctx->lat.on) b.build_latent(); else if (ctx->naf.on) b.build_naf(); else b.build();
     ok = b.ok; err = b.err;
   }
   long long n = (long long)B * ctx->cfg.in_nc * H * W;
@@ -932,12 +1113,12 @@ int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
   return IRSDE_OK;
 }
 
-void run_forward(irsde_ctx* ctx, Plan* p, cudaStream_t st) {
+void run_ops(irsde_ctx* ctx, Plan* p, std::vector<OpRec>& ops, cudaStream_t st) {
   if (!ctx->prof) {
-    for (auto& op : p->ops) op.fn(p, st);
+    for (auto& op : ops) op.fn(p, st);
     return;
   }
-  for (auto& op : p->ops) {
+  for (auto& op : ops) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
@@ -947,6 +1128,7 @@ void run_forward(irsde_ctx* ctx, Plan* p, cudaStream_t st) {
     ctx->prof_events.push_back({op.cat, op.flops, e0, e1, &op});
   }
 }
+void run_forward(irsde_ctx* ctx, Plan* p, cudaStream_t st) { run_ops(ctx, p, p->ops, st); }
 
 // default per-timestep scalars in fp32, same op order as the reference's 0-dim tensor math
 void fill_default_coeffs(irsde_ctx* c, int mode, std::vector<float>& tab) {
@@ -1074,6 +1256,59 @@ int irsde_create(const irsde_config* cfg, irsde_ctx** out) {
   return IRSDE_OK;
 }
 
+int irsde_create_latent_unet(const irsde_latent_unet_config* lcfg, irsde_ctx** out) {
+  if (!lcfg || !out) return fail(nullptr, IRSDE_ERR_INVALID, "null argument");
+  if (lcfg->ch < 1 || lcfg->in_ch < 1 || lcfg->out_ch < 1 || lcfg->n_levels < 1 || lcfg->n_levels > 8 || lcfg->embed_dim < 1)
+    return fail(nullptr, IRSDE_ERR_INVALID, "bad latent UNet configuration");
+  irsde_config cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.in_nc = lcfg->in_ch; cfg.out_nc = lcfg->out_ch; cfg.nf = 8; cfg.depth = lcfg->n_levels;
+  cfg.variant = IRSDE_NET_CONDITIONAL; cfg.precision = lcfg->precision; cfg.device = lcfg->device; cfg.reserved = lcfg->reserved;
+  int rc = irsde_create(&cfg, out);
+  if (rc) return rc;
+  irsde_ctx* c = *out;
+  c->lat.on = true;
+  c->lat.in_ch = lcfg->in_ch; c->lat.out_ch = lcfg->out_ch; c->lat.ch = lcfg->ch; c->lat.depth = lcfg->n_levels;
+  c->lat.embed = lcfg->embed_dim;
+  c->lat.mult[0] = 1;
+  for (int i = 0; i < lcfg->n_levels; ++i) c->lat.mult[i + 1] = lcfg->ch_mult[i];
+  return IRSDE_OK;
+}
+
+static int latent_run(irsde_ctx* ctx, bool decode, const float* in, float* out, int32_t B, int32_t H, int32_t W, void* stream) {
+  if (!ctx || !in || !out) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
+  if (!ctx->lat.on) return fail(ctx, IRSDE_ERR_STATE, "not a latent UNet context");
+  if (!ctx->finalized) return fail(ctx, IRSDE_ERR_STATE, "weights not finalized");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* p;
+  auto key = std::make_tuple(B, H, W);
+  bool existed = ctx->plans.find(key) != ctx->plans.end();
+  if (decode && !existed) return fail(ctx, IRSDE_ERR_STATE, "decode needs a preceding encode of the same shape (skip features)");
+  int rc = build_plan(ctx, B, H, W, &p);
+  if (rc) return rc;
+  p->cur.x = in; p->cur.mu = nullptr; p->cur.out = out;
+  p->cur.ss = nullptr; p->cur.t_ptr = p->d_zero; p->cur.ss_img_stride = 0;
+  run_ops(ctx, p, decode ? p->ops_dec : p->ops, st);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
+int irsde_latent_encode(irsde_ctx* ctx, const float* x, float* z, int32_t B, int32_t H, int32_t W, void* stream) {
+  return latent_run(ctx, false, x, z, B, H, W, stream);
+}
+int irsde_latent_decode(irsde_ctx* ctx, const float* z, float* out, int32_t B, int32_t H, int32_t W, void* stream) {
+  return latent_run(ctx, true, z, out, B, H, W, stream);
+}
+int irsde_latent_shape(irsde_ctx* ctx, int32_t H, int32_t W, int32_t* lat_h, int32_t* lat_w) {
+  if (!ctx || !ctx->lat.on || !lat_h || !lat_w) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  const int s = 1 << ctx->lat.depth;
+  const int Hp = H + (s - H % s) % s, Wp = W + (s - W % s) % s;
+  *lat_h = Hp >> (ctx->lat.depth - 1);
+  *lat_w = Wp >> (ctx->lat.depth - 1);
+  return IRSDE_OK;
+}
+
 int irsde_create_nafnet(const irsde_nafnet_config* ncfg, irsde_ctx** out) {
   if (!ncfg || !out) return fail(nullptr, IRSDE_ERR_INVALID, "null argument");
   if (ncfg->width < 4 || ncfg->width % 2 || ncfg->img_channel < 1 || ncfg->n_levels < 0 || ncfg->n_levels > 8 ||
@@ -1140,7 +1375,7 @@ int irsde_load_tensor(irsde_ctx* ctx, const char* name, const void* data, int32_
 int irsde_finalize_weights(irsde_ctx* ctx) {
   if (!ctx) return fail(nullptr, IRSDE_ERR_INVALID, "null ctx");
   cudaSetDevice(ctx->cfg.device);
-  auto specs = ctx->naf.on ? naf_param_specs(ctx->naf) : param_specs(ctx->cfg);
+  auto specs = ctx->lat.on ? lat_param_specs(ctx->lat) : (ctx->naf.on ? naf_param_specs(ctx->naf) : param_specs(ctx->cfg));
   for (auto& s : specs) {
     auto it = ctx->raw.find(s.name);
     if (it == ctx->raw.end()) return fail(ctx, IRSDE_ERR_STATE, "missing state-dict entry " + s.name);
@@ -1162,7 +1397,7 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
     pack_simt_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, ws, Cout, Cin, KH, KW);
     if (ctx->cfg.precision == IRSDE_PREC_BF16) {
       bool is_up = s.name.find(".3.1.weight") != std::string::npos;
-      bool is_stem = s.name == "init_conv.weight";
+      bool is_stem = s.name == "init_conv.weight" && KH == 7;
       int Cout_pad = (Cout + 7) / 8 * 8;
       long long nt = is_up ? (long long)16 * Cout * Cin : (is_stem ? (long long)7 * Cout * 64 : (long long)Cout_pad * Cin * KH * KW);
       bf16*& wt = ctx->w_tc[s.name];
@@ -1183,7 +1418,9 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
   struct TB { std::string pre; int rows; };
   std::vector<TB> tbs;
   int td = 0;
-  if (ctx->naf.on) {
+  if (ctx->lat.on) {
+    td = 1;  // no time conditioning in the autoencoder
+  } else if (ctx->naf.on) {
     td = 2 * ctx->naf.width;
     for (auto& b : naf_blocks(ctx->naf)) tbs.push_back({b.pre, 4 * b.c});
   } else {

@@ -94,6 +94,8 @@ def install(script_dir):
         latent = "latent" in os.path.basename(os.path.abspath(script_dir))
         import functools
         mods.ConditionalNAFNet = functools.partial(irsde_b200.ConditionalNAFNet, latent=latent) if latent else irsde_b200.ConditionalNAFNet
+    if hasattr(mods, "UNet"):
+        mods.UNet = irsde_b200.UNet
     return utils, mods
 
 

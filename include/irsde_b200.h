@@ -78,6 +78,18 @@ typedef struct {
   int32_t reserved;
 } irsde_nafnet_config;
 
+/* Refusion latent autoencoder: UNet(in_ch, out_ch, ch, ch_mult, embed_dim)
+ * (codes/config/latent-dehazing/models/modules/UNet_arch.py:17-57). */
+typedef struct {
+  int32_t in_ch, out_ch, ch;
+  int32_t n_levels;      /* len(ch_mult) <= 8 */
+  int32_t ch_mult[8];
+  int32_t embed_dim;
+  int32_t precision;     /* IRSDE_PREC_* */
+  int32_t device;
+  int32_t reserved;
+} irsde_latent_unet_config;
+
 /* Replaces `ConditionalUNet(in_nc,out_nc,nf,depth)` + `.to(device)`
  * (DenoisingUNet_arch.py:20, models/denoising_model.py:36). */
 int irsde_create(const irsde_config* cfg, irsde_ctx** out);
@@ -88,6 +100,15 @@ void irsde_destroy(irsde_ctx* ctx);
 const char* irsde_last_error(const irsde_ctx* ctx);
 /* "irsde_b200 <version> sm_100a" */
 const char* irsde_version(void);
+
+/* Latent autoencoder context (same weight-loading entry points).  encode replaces `UNet.encode(x) -> (z, h)`
+ * (UNet_arch.py:59-76): z is fp32 [B, embed_dim, lat_h, lat_w] (irsde_latent_shape); the skip list h stays inside the
+ * context.  decode replaces `UNet.decode(z, h)` (UNet_arch.py:78-91) and uses the skips of the last encode with the
+ * same (B, H, W); out is fp32 [B, out_ch, H, W]. */
+int irsde_create_latent_unet(const irsde_latent_unet_config* cfg, irsde_ctx** out);
+int irsde_latent_shape(irsde_ctx* ctx, int32_t H, int32_t W, int32_t* lat_h, int32_t* lat_w);
+int irsde_latent_encode(irsde_ctx* ctx, const float* x, float* z, int32_t B, int32_t H, int32_t W, void* stream);
+int irsde_latent_decode(irsde_ctx* ctx, const float* z, float* out, int32_t B, int32_t H, int32_t W, void* stream);
 
 /* Replaces `load_state_dict` (models/base_model.py:92-105): one call per state-dict entry,
  * `name` and `shape` exactly as in the reference state dict; `data` is fp32, host or device. */

@@ -519,3 +519,130 @@ def make_nafnet_weights(img_channel, width, middle_blk_num, enc_blk_nums, dec_bl
                 fan_in *= d
             P[name] = (torch.rand(shp, generator=g) * 2 - 1) * math.sqrt(3.0 / fan_in)
     return P
+
+
+# --------------------------------------------------------------------------------------
+# Refusion latent autoencoder: UNet.encode / UNet.decode   codes/config/latent-dehazing/models/modules/UNet_arch.py:17-97
+# --------------------------------------------------------------------------------------
+
+
+def _res_block_notime(P, pre, x):
+    """ResBlock with time_emb_dim=None (module_util.py:125-146: no scale/shift)."""
+    h = _silu(F.conv2d(x, P[pre + "block1.proj.weight"], padding=1))
+    h = _silu(F.conv2d(h, P[pre + "block2.proj.weight"], padding=1))
+    if (pre + "res_conv.weight") in P:
+        x = F.conv2d(x, P[pre + "res_conv.weight"])
+    return h + x
+
+
+def latent_unet_encode(P, x, ch_mult):
+    """UNet.encode (UNet_arch.py:59-76): returns (z, h) with h the list of skip tensors."""
+    depth = len(ch_mult)
+    H, W = x.shape[2:]
+    s = 2 ** depth
+    x = F.pad(x, (0, (s - W % s) % s, 0, (s - H % s) % s), "reflect")
+    x = F.conv2d(x, P["init_conv.weight"], padding=1)
+    h = [x]
+    for i in range(depth):
+        pre = "encoder.%d." % i
+        x = _res_block_notime(P, pre + "0.", x)
+        h.append(x)
+        x = _res_block_notime(P, pre + "1.", x)
+        if i == depth - 1:
+            x = linear_attention(P, pre + "2.fn.", x)
+        h.append(x)
+        if i != depth - 1:
+            x = F.conv2d(x, P[pre + "3.weight"], P[pre + "3.bias"], stride=2, padding=1)
+        else:
+            x = F.conv2d(x, P[pre + "3.weight"], padding=1)
+    return F.conv2d(x, P["latent_conv.weight"]), h
+
+
+def latent_unet_decode(P, z, h, ch_mult, H, W):
+    """UNet.decode (UNet_arch.py:78-91)."""
+    depth = len(ch_mult)
+    x = F.conv2d(z, P["post_latent_conv.weight"])
+    for i in range(depth):
+        pre = "decoder.%d." % i
+        x = torch.cat([x, h[-(i * 2 + 1)]], dim=1)
+        x = _res_block_notime(P, pre + "0.", x)
+        x = torch.cat([x, h[-(i * 2 + 2)]], dim=1)
+        x = _res_block_notime(P, pre + "1.", x)
+        if i == 0:
+            x = linear_attention(P, pre + "2.fn.", x)
+        if i != depth - 1:
+            x = F.interpolate(x, scale_factor=2, mode="nearest")
+            x = F.conv2d(x, P[pre + "3.1.weight"], P[pre + "3.1.bias"], padding=1)
+        else:
+            x = F.conv2d(x, P[pre + "3.weight"], padding=1)
+    x = F.conv2d(x + h[0], P["final_conv.weight"], P["final_conv.bias"], padding=1)
+    return x[..., :H, :W]
+
+
+def latent_unet_param_shapes(in_ch, out_ch, ch, ch_mult, embed_dim):
+    """State-dict names -> shapes in the reference's registration order (UNet_arch.py:18-51)."""
+    S = {}
+    depth = len(ch_mult)
+    m = [1] + list(ch_mult)
+    S["init_conv.weight"] = (ch, in_ch, 3, 3)
+
+    def rb(pre, ci, co):
+        S[pre + "block1.proj.weight"] = (co, ci, 3, 3)
+        S[pre + "block2.proj.weight"] = (co, co, 3, 3)
+        if ci != co:
+            S[pre + "res_conv.weight"] = (co, ci, 1, 1)
+
+    def la(pre, c):
+        S[pre + "fn.fn.to_qkv.weight"] = (384, c, 1, 1)
+        S[pre + "fn.fn.to_out.0.weight"] = (c, 128, 1, 1)
+        S[pre + "fn.fn.to_out.0.bias"] = (c,)
+        S[pre + "fn.fn.to_out.1.g"] = (1, c, 1, 1)
+        S[pre + "fn.norm.g"] = (1, c, 1, 1)
+
+    dec = []
+    for i in range(depth):
+        di, do = ch * m[i], ch * m[i + 1]
+        pre = "encoder.%d." % i
+        rb(pre + "0.", di, di)
+        rb(pre + "1.", di, di)
+        if i == depth - 1:
+            la(pre + "2.", di)
+        if i != depth - 1:
+            S[pre + "3.weight"] = (do, di, 4, 4)
+            S[pre + "3.bias"] = (do,)
+        else:
+            S[pre + "3.weight"] = (do, di, 3, 3)
+        dec.insert(0, (i, di, do))
+    for j, (i, di, do) in enumerate(dec):
+        pre = "decoder.%d." % j
+        rb(pre + "0.", do + di, do)
+        rb(pre + "1.", do + di, do)
+        if i == depth - 1:
+            la(pre + "2.", do)
+        if i != 0:
+            S[pre + "3.1.weight"] = (di, do, 3, 3)
+            S[pre + "3.1.bias"] = (di,)
+        else:
+            S[pre + "3.weight"] = (di, do, 3, 3)
+    mid = ch * m[-1]
+    S["latent_conv.weight"] = (embed_dim, mid, 1, 1)
+    S["post_latent_conv.weight"] = (mid, embed_dim, 1, 1)
+    S["final_conv.weight"] = (out_ch, ch, 3, 3)
+    S["final_conv.bias"] = (out_ch,)
+    return S
+
+
+def make_latent_unet_weights(in_ch, out_ch, ch, ch_mult, embed_dim, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    P = {}
+    for name, shp in latent_unet_param_shapes(in_ch, out_ch, ch, ch_mult, embed_dim).items():
+        if name.endswith(".g"):
+            P[name] = 1.0 + 0.1 * torch.randn(shp, generator=g)
+        elif name.endswith("bias"):
+            P[name] = 0.05 * torch.randn(shp, generator=g)
+        else:
+            fan_in = 1
+            for d in shp[1:]:
+                fan_in *= d
+            P[name] = (torch.rand(shp, generator=g) * 2 - 1) * math.sqrt(3.0 / fan_in)
+    return P

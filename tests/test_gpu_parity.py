@@ -406,3 +406,40 @@ def test_full_size_properties_bf16(lib):
         eps_true = sde.get_real_noise(x, x0, t)
         x = sde._native_step(lib._lib.MODE_POSTERIOR, x, sde.mu, eps_true, torch.randn_like(x), t)
     assert _maxdiff(x, x0) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# Refusion latent autoencoder UNet.encode / decode
+# ------------------------------------------------------------------------------------------------
+def test_latent_unet_fp32_vs_reference(lib):
+    import os
+    dev = _dev()
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_latent.pt"), weights_only=False)
+    net = lib.UNet(precision="fp32", **g["cfg"])
+    assert list(net.state_dict().keys()) == list(g["state"].keys())
+    net.load_state_dict(g["state"], strict=True)
+    net = net.to(dev)
+    z, h = net.encode(g["x"].to(dev))
+    assert z.shape == g["z"].shape and _maxdiff(z, g["z"]) < 1e-4   # ragged 21x30 -> reflect pad 24x32, latent 12x16
+    assert _maxdiff(net.decode(g["z2"].to(dev), h), g["y"]) < 1e-4   # decode of a perturbed latent with the LQ's skips
+    assert _maxdiff(net(g["x"].to(dev)), g["y_id"]) < 1e-4
+
+
+def test_latent_unet_bf16_and_real_architecture(lib):
+    """The shipped checkpoint's architecture (ch=8, ch_mult=[4,8,8,16], embed 8) with random weights: fp32 vs oracle
+    <= 2e-4, bf16 (tcgen05 path) within 4 % of the output scale."""
+    dev = _dev()
+    cfg = dict(in_ch=3, out_ch=3, ch=8, ch_mult=[4, 8, 8, 16], embed_dim=8)
+    P = O.make_latent_unet_weights(3, 3, 8, [4, 8, 8, 16], 8, seed=2)
+    g = torch.Generator().manual_seed(3)
+    x = torch.rand(2, 3, 70, 90, generator=g)
+    zo, ho = O.latent_unet_encode(P, x, cfg["ch_mult"])
+    yo = O.latent_unet_decode(P, zo, ho, cfg["ch_mult"], 70, 90)
+    for prec, tz, ty in (("fp32", 2e-4, 2e-4), ("bf16", 4e-2 * zo.abs().max().item(), 4e-2 * yo.abs().max().item())):
+        net = lib.UNet(precision=prec, **cfg)
+        net.load_state_dict(P, strict=True)
+        net = net.to(dev)
+        z, h = net.encode(x.to(dev))
+        assert _maxdiff(z, zo) < tz, (prec, _maxdiff(z, zo))
+        y = net.decode(zo.to(dev), h)
+        assert _maxdiff(y, yo) < ty, (prec, _maxdiff(y, yo))

@@ -109,3 +109,44 @@ def test_nafnet_oracle_vs_reference():
         _close(yv, g["y_vec"], 1e-5)
         shapes = O.nafnet_param_shapes(c["img_channel"], c["width"], c["middle_blk_num"], c["enc_blk_nums"], c["dec_blk_nums"])
         assert list(shapes) == list(g["state"])
+
+
+def test_latent_unet_oracle_vs_reference():
+    import os
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_latent.pt"), weights_only=False)
+    c = g["cfg"]
+    z, h = O.latent_unet_encode(g["state"], g["x"], c["ch_mult"])
+    _close(z, g["z"], 1e-5)
+    y = O.latent_unet_decode(g["state"], g["z2"], h, c["ch_mult"], g["x"].shape[2], g["x"].shape[3])
+    _close(y, g["y"], 1e-5)
+    shapes = O.latent_unet_param_shapes(c["in_ch"], c["out_ch"], c["ch"], c["ch_mult"], c["embed_dim"])
+    assert list(shapes) == list(g["state"])
+
+
+def test_latent_unet_oracle_real_checkpoint():
+    """The shipped latent-dehazing.pth (2.0 M params) through the reference module vs the oracle (needs the reference)."""
+    import os
+    import sys
+    ck = "/root/reference/codes/config/latent-dehazing/pretrained_models/latent-dehazing.pth"
+    if not os.path.exists(ck):
+        import pytest
+        pytest.skip("reference checkout not available")
+    sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
+    from make_golden_latent import load_unet_arch
+    arch = load_unet_arch()
+    sd = torch.load(ck, map_location="cpu", weights_only=True)
+    net = arch.UNet(in_ch=3, out_ch=3, ch=8, ch_mult=[4, 8, 8, 16], embed_dim=8).eval()
+    net.load_state_dict(sd, strict=True)
+    x = torch.rand(1, 3, 50, 70, generator=torch.Generator().manual_seed(0))
+    with torch.no_grad():
+        z, h = net.encode(x)
+        y = net.decode(z, h)
+    zo, ho = O.latent_unet_encode(sd, x, [4, 8, 8, 16])
+    _close(zo, z, 1e-4)
+    for a, b in zip(ho, h):
+        _close(a, b, 1e-3)
+    # decode is NOT compared for this checkpoint: on such inputs the reference's own fp32 and fp64 decodes differ by
+    # O(100) (ill-conditioned trained weights), so no fp32 restatement can be pinned there; decode parity is pinned on
+    # the well-conditioned random-weight fixture (test_latent_unet_oracle_vs_reference).
+    assert y.shape == x.shape
+    assert list(O.latent_unet_param_shapes(3, 3, 8, [4, 8, 8, 16], 8)) == list(sd)
