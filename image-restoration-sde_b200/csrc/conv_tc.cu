@@ -944,6 +944,13 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   while ((1 << P.logBW) < P.BW) P.logBW++;
   P.tilesW = (Win + P.BW - 1) / P.BW;
   P.tilesH = (Hin + P.BH - 1) / P.BH;
+  // Small problems (NAFNet's 16x16 levels, sharded deep UNet levels): fewer tiles than half the SMs means a handful
+  // of CTAs stream all the weights; narrower N tiles spread that over more SMs.  Tap mode 0 accumulates in the same
+  // K order for every BN, so results do not depend on this choice (and hence not on the batch size).
+  if (g_persist && !patch && !rows && !P.qsm && !nchw_out) {
+    const int tm = P.tilesW * P.tilesH * B * nphases;
+    while (BN > 64 && Cout % (BN / 2) == 0 && (long long)tm * ((Cout + BN - 1) / BN) < 74) BN >>= 1;
+  }
   d->BN = BN;
   d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
   d->tiles_m = P.tilesW * P.tilesH * B * nphases;

@@ -61,25 +61,27 @@ __global__ void __launch_bounds__(256) dwgate_kernel(const T* __restrict__ x, in
 }
 
 // mean over pixels -> 1x1 conv (c x c mat-vec + bias): sca[b][o]            (DenoisingNAFNet_arch.py:29-33)
+// grid (ceil(c/8), B): every block re-derives the c means (c*nchunks floats, L2 resident) and its 8 warps each own
+// one output row, so the c x c weight matrix is streamed by c/8 SMs instead of one.
 __global__ void __launch_bounds__(256) sca_kernel(const float* __restrict__ partial, const float* __restrict__ w,
                                                   const float* __restrict__ bias, float* __restrict__ sca, int c, int nchunks,
                                                   int N) {
   extern __shared__ float mean_s[];
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float s = 0.f;
     for (int k = 0; k < nchunks; ++k) s += partial[((long long)b * nchunks + k) * c + ch];
     mean_s[ch] = s / (float)N;
   }
   __syncthreads();
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int o = warp; o < c; o += nw) {
-    float s = 0.f;
-    for (int k = lane; k < c; k += 32) s += w[(long long)o * c + k] * mean_s[k];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int o = blockIdx.x * 8 + warp;
+  if (o >= c) return;
+  float s = 0.f;
+  for (int k = lane; k < c; k += 32) s += w[(long long)o * c + k] * mean_s[k];
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-    if (lane == 0) sca[(long long)b * c + o] = s + bias[o];
-  }
+  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+  if (lane == 0) sca[(long long)b * c + o] = s + bias[o];
 }
 
 // x[b,p,ch] *= sca[b][ch]   (in place; the "x * self.sca(x)" of :67)
@@ -153,7 +155,7 @@ template void launch_dwgate<float>(const float*, int, const float*, const float*
 template void launch_dwgate<bf16>(const bf16*, int, const float*, const float*, bf16*, int, float*, int, int, int, int, cudaStream_t);
 
 void launch_sca(const float* partial, const float* w, const float* bias, float* sca, int B, int c, int nchunks, int N, cudaStream_t st) {
-  sca_kernel<<<B, 256, c * sizeof(float), st>>>(partial, w, bias, sca, c, nchunks, N);
+  sca_kernel<<<dim3((c + 7) / 8, B), 256, c * sizeof(float), st>>>(partial, w, bias, sca, c, nchunks, N);
 }
 
 template <typename T>

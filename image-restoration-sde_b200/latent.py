@@ -94,8 +94,8 @@ class _LatContext(_lib.Context):
 class LatentSkips:
     """Opaque stand-in for the reference's skip list ``h``: (owner module, input shape)."""
 
-    def __init__(self, owner, shape):
-        self.owner, self.shape = owner, tuple(shape)
+    def __init__(self, owner, shape, gen):
+        self.owner, self.shape, self.gen = owner, tuple(shape), gen
 
 
 class UNet(ConditionalUNet):
@@ -153,12 +153,16 @@ class UNet(ConditionalUNet):
             _lib.check(ctx.L.irsde_latent_encode(ctx.h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(z.data_ptr()), B, H, W,
                                                  ctypes.c_void_p(st)), ctx.h)
         self.H, self.W = H, W
-        return z, LatentSkips(self, (B, H, W))
+        self._gen = getattr(self, "_gen", 0) + 1
+        return z, LatentSkips(self, (B, H, W), self._gen)
 
     @torch.no_grad()
     def decode(self, x, h):
         if not isinstance(h, LatentSkips) or h.owner is not self:
             raise ValueError("decode needs the skip handle returned by this module's encode()")
+        if h.gen != getattr(self, "_gen", 0):
+            raise RuntimeError("stale skip handle: a later encode() overwrote the device-resident skips "
+                               "(one outstanding encode per module)")
         B, H, W = h.shape
         x = x.contiguous().float()
         ctx = self.sync_weights(x.device)

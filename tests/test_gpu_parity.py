@@ -423,6 +423,10 @@ def test_latent_unet_fp32_vs_reference(lib):
     assert z.shape == g["z"].shape and _maxdiff(z, g["z"]) < 1e-4   # ragged 21x30 -> reflect pad 24x32, latent 12x16
     assert _maxdiff(net.decode(g["z2"].to(dev), h), g["y"]) < 1e-4   # decode of a perturbed latent with the LQ's skips
     assert _maxdiff(net(g["x"].to(dev)), g["y_id"]) < 1e-4
+    _, h2 = net.encode(g["x"].to(dev))
+    with pytest.raises(RuntimeError):      # the skips of `h` were overwritten by the later encode: must not decode silently
+        net.decode(g["z2"].to(dev), h)
+    assert _maxdiff(net.decode(g["z2"].to(dev), h2), g["y"]) < 1e-4
 
 
 def test_latent_unet_bf16_and_real_architecture(lib):
