@@ -80,6 +80,19 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def ncu_traffic_per_launch():
+    """Mean DRAM bytes (read + write) per tcgen05 conv launch from the committed `ncu --set full` capture of this
+    workload (profiles/), or None when the summary is absent.  Not measured live: ncu cannot run inside a timed bench."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_final_conv_tc_ncu_full_one_step.csv")
+    try:
+        rows = list(csv.DictReader(open(path)))[1:]   # first row holds the units (Mbyte)
+        tot = sum(float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"]) for r in rows)
+        return tot * 1e6 / len(rows)
+    except Exception:
+        return None
+
+
 def usable_cores():
     """Host cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
     n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
@@ -272,7 +285,9 @@ def run_b200(args):
                     "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
                     "peak_source": peak_src if k == 0 else "nominal fp32 FMA peak",
                     "flops_per_launch": fl_a[k] / n_a[k], "avg_launch_ms": ms_a[k] / n_a[k], "launches": int(n_a[k]),
-                    "share_of_step": ms_a[k] / sum(ms_a), "traffic": None,
+                    "share_of_step": ms_a[k] / sum(ms_a), "traffic": ncu_traffic_per_launch() if k == 0 else None,
+                    "traffic_source": "profiles/r01_final_conv_tc_ncu_full_one_step.csv: mean dram read+write bytes per "
+                                      "launch over one step's launches, ncu --set full capture of this workload",
                     "how": "CUDA events around each launch, %d sampler steps, non-graph pass after the timed region" % prof_steps}
 
     # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same workload on host cores

@@ -16,9 +16,9 @@ NUM_COEF = 8
 
 # every symbol include/irsde_b200.h declares
 SYMBOLS = ["irsde_create", "irsde_create_nafnet", "irsde_create_latent_unet", "irsde_latent_shape", "irsde_latent_encode",
-           "irsde_latent_decode", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
+           "irsde_latent_decode", "irsde_tensor2img_u8", "irsde_img2tensor_u8", "irsde_sqerr_u8", "irsde_ssim_workspace", "irsde_ssim_u8", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
            "irsde_finalize_weights", "irsde_set_schedule", "irsde_set_coeffs", "irsde_noise_fn", "irsde_step",
-           "irsde_reverse", "irsde_noise_state", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
+           "irsde_reverse", "irsde_noise_state", "irsde_noise_state_images", "irsde_set_image_base", "irsde_set_image_uids", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
            "irsde_profile_end"]
 
 
@@ -65,6 +65,12 @@ def load():
     L.irsde_reverse.restype = ctypes.c_int
     L.irsde_noise_state.argtypes = [vp, vp, vp, i64, u64, vp]
     L.irsde_noise_state.restype = ctypes.c_int
+    L.irsde_noise_state_images.argtypes = [vp, vp, vp, i32, i64, u64, vp]
+    L.irsde_noise_state_images.restype = ctypes.c_int
+    L.irsde_set_image_base.argtypes = [vp, u64]
+    L.irsde_set_image_base.restype = ctypes.c_int
+    L.irsde_set_image_uids.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), i32, vp]
+    L.irsde_set_image_uids.restype = ctypes.c_int
     L.irsde_launch_count.argtypes = [vp]
     L.irsde_launch_count.restype = i64
     L.irsde_device_bytes.argtypes = [vp]

@@ -84,7 +84,9 @@ int dwgate_chunks(int H, int W);
 template <typename T>
 void launch_dwgate(const T* x, int x_pitch, const float* w, const float* bias, T* gate, int g_pitch, float* partial, int B,
                    int H, int W, int c, cudaStream_t st);
-void launch_sca(const float* partial, const float* w, const float* bias, float* sca, int B, int c, int nchunks, int N, cudaStream_t st);
+template <typename T>
+void launch_sca_scale(const float* partial, const float* w, const float* bias, float* sca, T* g, int g_pitch, int B, int c,
+                      int nchunks, int N, int* launches, cudaStream_t st);
 template <typename T>
 void launch_scale_channels(T* x, int pitch, const float* sca, int B, int N, int c, cudaStream_t st);
 template <typename T>
@@ -121,13 +123,17 @@ struct StepState {
   int i;               // executed-step index (z slice)
   const float* z;      // pre-drawn noise [T][n] or null (in-kernel Philox)
   unsigned long long seed;
+  unsigned long long uid_base;  // uid of the batch's first image (Philox is keyed per image)
+  const unsigned long long* uids;  // explicit per-image uids [B] or null (uid = uid_base + b)
 };
 void launch_sde_update(int mode, const float* x, const float* mu, const float* noise, const float* z, long long z_stride,
                        const float* coef, const StepState* st_dev, int t_host, float* out, long long n, uint64_t seed,
-                       cudaStream_t st);
+                       long long img_elems, uint64_t uid_base, cudaStream_t st);
 void launch_advance_step(StepState* st_dev, cudaStream_t st);
-void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned long long seed, cudaStream_t st);
-void launch_noise_state(const float* mu, float* out, long long n, float max_sigma, uint64_t seed, cudaStream_t st);
+void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned long long seed, unsigned long long uid_base,
+                     const unsigned long long* uids, cudaStream_t st);
+void launch_noise_state(const float* mu, float* out, long long n, float max_sigma, uint64_t seed, long long img_elems,
+                        uint64_t uid_base, const unsigned long long* uids, cudaStream_t st);
 // layout helpers for the tensor-core path
 template <typename T>
 void launch_space_to_depth(const T* in, int in_pitch, T* out, int B, int H, int W, int C, cudaStream_t st);
@@ -149,5 +155,14 @@ void tc_conv_set_runtime(TcConvDesc*, const float* ss, const int* t_ptr, int ss_
 void tc_conv_set_out_nchw(TcConvDesc*, float* out, int cropH, int cropW);  // out==nullptr at create => fp32 NCHW output
 int tc_conv_launch(TcConvDesc*, cudaStream_t st);  // returns number of launches (1), <0 on error
 bool tc_init(std::string* err);                    // resolves cuTensorMapEncodeTiled
+
+// ---- image conversion / metrics (imaging.cu) ---------------------------------------------------
+void launch_tensor2img(const float* in, unsigned char* out, int B, int C, int H, int W, double lo, double hi, cudaStream_t st);
+void launch_img2tensor(const unsigned char* in, float* out, int B, int C, int H, int W, cudaStream_t st);
+void launch_sqerr_u8(const unsigned char* a, const unsigned char* b, int B, int H, int W, int C, int crop, unsigned long long* out,
+                     cudaStream_t st);
+long long ssim_partial_count(int H, int W, int C, int crop);
+void launch_ssim_u8(const unsigned char* a, const unsigned char* b, int B, int H, int W, int C, int crop, double* partial, double* out,
+                    cudaStream_t st);
 
 }  // namespace irsde

@@ -188,8 +188,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32
     k1 += 0xBB67AE85u;
   }
 }
-__device__ __forceinline__ void normal4(uint64_t seed, uint64_t ctr, uint32_t stream, float out[4]) {
-  uint32_t c[4] = {(uint32_t)ctr, (uint32_t)(ctr >> 32), stream, 0x1234567u};
+// Four N(0,1) draws of Philox block `blk` of image `uid` at stream `stream` (= timestep; 0xffffffff for noise_state).
+// The counter is (block within the image, image uid, stream): what an image receives depends only on (seed, uid, t,
+// element index inside the image) - not on the batch it travels in, its position in it, or the rank that owns it.
+__device__ __forceinline__ void normal4(uint64_t seed, uint64_t uid, uint32_t blk, uint32_t stream, float out[4]) {
+  uint32_t c[4] = {blk, (uint32_t)uid, stream, 0x1234567u ^ (uint32_t)(uid >> 32)};
   philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
   const float two_pow_m32 = 2.3283064365386963e-10f;
   float u0 = ((float)c[0] + 0.5f) * two_pow_m32, u1 = ((float)c[1] + 0.5f) * two_pow_m32;
@@ -204,6 +207,26 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint64_t ctr, uint32_t st
   out[1] = r0 * s0;
   out[2] = r1 * c1;
   out[3] = r1 * s1;
+}
+
+// z for the 4 consecutive elements i0..i0+3 of a [B][img_elems] buffer (a group may straddle two images or two
+// Philox blocks when img_elems % 4 != 0; it is one block otherwise).
+__device__ __forceinline__ void image_normals(uint64_t seed, uint64_t uid_base, const unsigned long long* __restrict__ uids,
+                                              long long i0, long long img_elems, uint32_t stream, float zr[4]) {
+  long long b = i0 / img_elems, j = i0 - b * img_elems;
+  float blk[4];
+  long long cur_b = -1, cur_blk = -1;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (j == img_elems) { j = 0; ++b; }
+    const long long q = j >> 2;
+    if (b != cur_b || q != cur_blk) {
+      normal4(seed, uids ? (uint64_t)uids[b] : uid_base + (uint64_t)b, (uint32_t)q, stream, blk);
+      cur_b = b; cur_blk = q;
+    }
+    zr[k] = blk[j & 3];
+    ++j;
+  }
 }
 
 __device__ __forceinline__ float sde_update_one(int mode, const float* c, float x, float mu, float eps, float z) {
@@ -242,20 +265,22 @@ __device__ __forceinline__ float sde_update_one(int mode, const float* c, float 
 __global__ void sde_update_kernel(int mode, const float* __restrict__ x, const float* __restrict__ mu,
                                   const float* __restrict__ noise, const float* __restrict__ z, long long z_stride,
                                   const float* __restrict__ coef, const StepState* __restrict__ stp, int t_host,
-                                  float* __restrict__ out, long long n, uint64_t seed) {
+                                  float* __restrict__ out, long long n, uint64_t seed, long long img_elems,
+                                  uint64_t uid_base) {
+  const unsigned long long* uids = nullptr;
   int t = stp ? stp->t : t_host;
   int si = stp ? stp->i : 0;
   float c[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) c[k] = coef[t * 8 + k];
   bool need_z = (mode == 0 || mode == 2 || mode == 3);
-  if (stp) { z = stp->z; seed = stp->seed; }
+  if (stp) { z = stp->z; seed = stp->seed; uid_base = stp->uid_base; uids = stp->uids; }
   const float* zz = z ? z + (long long)si * z_stride : nullptr;
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
   long long i0 = q * 4;
   if (i0 >= n) return;
   float zr[4] = {0.f, 0.f, 0.f, 0.f};
-  if (need_z && !zz) normal4(seed, (uint64_t)q, (uint32_t)t, zr);
+  if (need_z && !zz) image_normals(seed, uid_base, uids, i0, img_elems, (uint32_t)t, zr);
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     long long i = i0 + k;
@@ -269,41 +294,49 @@ __global__ void sde_update_kernel(int mode, const float* __restrict__ x, const f
 
 void launch_sde_update(int mode, const float* x, const float* mu, const float* noise, const float* z, long long z_stride,
                        const float* coef, const StepState* st_dev, int t_host, float* out, long long n, uint64_t seed,
-                       cudaStream_t st) {
+                       long long img_elems, uint64_t uid_base, cudaStream_t st) {
   long long groups = (n + 3) / 4;
   sde_update_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(mode, x, mu, noise, z, z_stride, coef, st_dev,
-                                                                      t_host, out, n, seed);
+                                                                      t_host, out, n, seed, img_elems > 0 ? img_elems : n,
+                                                                      uid_base);
 }
 
 __global__ void advance_step_kernel(StepState* s) {
   s->t -= 1;
   s->i += 1;
 }
-__global__ void set_step_kernel(StepState* s, int t, int i, const float* z, unsigned long long seed) {
+__global__ void set_step_kernel(StepState* s, int t, int i, const float* z, unsigned long long seed, unsigned long long uid_base,
+                                const unsigned long long* uids) {
   s->t = t;
   s->i = i;
   s->z = z;
   s->seed = seed;
+  s->uid_base = uid_base;
+  s->uids = uids;
 }
 void launch_advance_step(StepState* st_dev, cudaStream_t st) { advance_step_kernel<<<1, 1, 0, st>>>(st_dev); }
-void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned long long seed, cudaStream_t st) {
-  set_step_kernel<<<1, 1, 0, st>>>(st_dev, t, i, z, seed);
+void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned long long seed, unsigned long long uid_base,
+                     const unsigned long long* uids, cudaStream_t st) {
+  set_step_kernel<<<1, 1, 0, st>>>(st_dev, t, i, z, seed, uid_base, uids);
 }
 
 __global__ void noise_state_kernel(const float* __restrict__ mu, float* __restrict__ out, long long n, float max_sigma,
-                                   uint64_t seed) {
+                                   uint64_t seed, long long img_elems, uint64_t uid_base,
+                                   const unsigned long long* __restrict__ uids) {
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long i0 = q * 4;
   if (i0 >= n) return;
   float zr[4];
-  normal4(seed, (uint64_t)q, 0xffffffffu, zr);
+  image_normals(seed, uid_base, uids, i0, img_elems, 0xffffffffu, zr);
 #pragma unroll
   for (int k = 0; k < 4; ++k)
     if (i0 + k < n) out[i0 + k] = mu[i0 + k] + zr[k] * max_sigma;
 }
-void launch_noise_state(const float* mu, float* out, long long n, float max_sigma, uint64_t seed, cudaStream_t st) {
+void launch_noise_state(const float* mu, float* out, long long n, float max_sigma, uint64_t seed, long long img_elems,
+                        uint64_t uid_base, const unsigned long long* uids, cudaStream_t st) {
   long long groups = (n + 3) / 4;
-  noise_state_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(mu, out, n, max_sigma, seed);
+  noise_state_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(mu, out, n, max_sigma, seed, img_elems > 0 ? img_elems : n,
+                                                                       uid_base, uids);
 }
 
 // =============================================================================================

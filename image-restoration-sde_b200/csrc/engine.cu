@@ -106,6 +106,9 @@ struct irsde_ctx {
   float* coef_dev[IRSDE_NUM_MODES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   std::map<std::tuple<int, int, int>, Plan*> plans;
   long long launches = 0;
+  unsigned long long image_base = 0;  // uid of the first image of the next batch (Philox key; irsde_set_image_base)
+  unsigned long long* d_uids = nullptr;  // explicit per-image uids (irsde_set_image_uids), capacity MAX_UIDS
+  int n_uids = 0;                        // 0: uid = image_base + b
   long long dev_bytes = 0;
   std::vector<void*> allocs;
   bool tc_ok = false;
@@ -510,7 +513,8 @@ struct Builder {
     bool nchw = out_nchw_slot != nullptr;
     if constexpr (std::is_same<T, bf16>::value) {
       bool shape_ok = (K == 3 && stride == 1 && pad == 1) || (K == 1 && stride == 1 && pad == 0 && up == 1) ||
-                      (K == 4 && stride == 2 && pad == 1 && up == 1 && Hin % 2 == 0 && Win % 2 == 0);
+                      (K == 4 && stride == 2 && pad == 1 && up == 1 && Hin % 2 == 0 && Win % 2 == 0) ||
+                      (K == 2 && stride == 2 && pad == 0 && up == 1 && Hin % 2 == 0 && Win % 2 == 0);
       bool stem_tc = ctx->use_tc && stem_padded && K == 7 && Cout % 8 == 0 && out.pitch % 8 == 0;
       if (stem_tc) {
         const bf16* wt = ctx->w_tc[wname];
@@ -543,9 +547,13 @@ struct Builder {
           for (int a = 0; a < 2; ++a) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{a - 1, q - 1, 0};
         } else if (K == 1) {
           taps[ntaps++] = TcTap{0, 0, 0};
-        } else {  // 4x4 stride 2 pad 1 over space-to-depth planes
+        } else {  // stride 2 over space-to-depth planes: 4x4 pad 1 (UNet Downsample) or 2x2 pad 0 (NAFNet downs)
           static const int PY[4] = {1, 0, 1, 0}, DH[4] = {-1, 0, 0, 1};
-          for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) taps[ntaps++] = TcTap{DH[r], DH[q], PY[r] * 2 + PY[q]};
+          if (K == 4) {
+            for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) taps[ntaps++] = TcTap{DH[r], DH[q], PY[r] * 2 + PY[q]};
+          } else {
+            for (int r = 0; r < 2; ++r) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{0, 0, r * 2 + q};
+          }
           planes = 4; Ha = Hin / 2; Wa = Win / 2; a_pitch = in.C;
           bf16* s2d = tmp((long long)plan->B * Hin * Win * in.C);
           int Bc = plan->B, Cc = in.C;
@@ -841,9 +849,9 @@ struct Builder {
       const int nch = dwgate_chunks(H, W);
       plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
         launch_dwgate<T>(t2, 2 * c, w2, bb2, g, c, partial, B, H, W, c, st);
-        launch_sca(partial, ws, bs, sca, B, c, nch, N, st);
-        launch_scale_channels<T>(g, c, sca, B, N, c, st);
-        cx->launches += 3;
+        int nl = 0;
+        launch_sca_scale<T>(partial, ws, bs, sca, g, c, B, c, nch, N, &nl, st);
+        cx->launches += 1 + nl;
       }});
       plan->ops.back().label = pre + "dw3x3+gate+sca";
       plan->ops.back().bytes = (double)npix * (2 * c + c + 2 * c) * sizeof(T);
@@ -1501,7 +1509,7 @@ int irsde_step(irsde_ctx* ctx, int32_t mode, const float* x, const float* mu, co
   if (need_z && !z) return fail(ctx, IRSDE_ERR_INVALID, "z required for stochastic modes");
   if (mode <= IRSDE_MODE_POSTERIOR && !mu) return fail(ctx, IRSDE_ERR_INVALID, "mu required for IRSDE modes");
   cudaSetDevice(ctx->cfg.device);
-  launch_sde_update(mode, x, mu, noise, z, 0, ctx->coef_dev[mode], nullptr, t, out, n, 0, (cudaStream_t)stream);
+  launch_sde_update(mode, x, mu, noise, z, 0, ctx->coef_dev[mode], nullptr, t, out, n, 0, 0, 0, (cudaStream_t)stream);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
   return IRSDE_OK;
@@ -1533,14 +1541,16 @@ int irsde_reverse(irsde_ctx* ctx, int32_t mode, const float* xT, const float* mu
   }
   rc = ensure_chain_table(ctx, p, ctx->T, st);
   if (rc) return rc;
-  launch_set_step(p->d_step, T, 0, z, seed, st);
+  if (ctx->n_uids && ctx->n_uids != B) return fail(ctx, IRSDE_ERR_INVALID, "irsde_set_image_uids count does not match the batch");
+  launch_set_step(p->d_step, T, 0, z, seed, ctx->image_base, ctx->n_uids ? ctx->d_uids : nullptr, st);
   ctx->launches++;
   p->cur.x = p->x_state; p->cur.mu = p->mu_buf; p->cur.out = p->eps_buf;
   p->cur.ss = p->chain_table; p->cur.t_ptr = &p->d_step->t; p->cur.ss_img_stride = 0;
   const float* mu_arg = irs ? p->mu_buf : nullptr;
   auto one_step = [&](cudaStream_t s) {
     run_forward(ctx, p, s);
-    launch_sde_update(mode, p->x_state, mu_arg, p->eps_buf, nullptr, n, ctx->coef_dev[mode], p->d_step, 0, p->x_state, n, 0, s);
+    launch_sde_update(mode, p->x_state, mu_arg, p->eps_buf, nullptr, n, ctx->coef_dev[mode], p->d_step, 0, p->x_state, n, 0,
+                      n / B, 0, s);
     launch_advance_step(p->d_step, s);
     ctx->launches += 2;
   };
@@ -1580,9 +1590,43 @@ int irsde_noise_state(irsde_ctx* ctx, const float* mu, float* out, int64_t n, ui
   if (!ctx || !mu || !out) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
   if (!ctx->have_sched) return fail(ctx, IRSDE_ERR_STATE, "schedule not set");
   cudaSetDevice(ctx->cfg.device);
-  launch_noise_state(mu, out, n, ctx->max_sigma, seed, (cudaStream_t)stream);
+  launch_noise_state(mu, out, n, ctx->max_sigma, seed, n, ctx->image_base, nullptr, (cudaStream_t)stream);
   ctx->launches++;
   CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
+int irsde_noise_state_images(irsde_ctx* ctx, const float* mu, float* out, int32_t B, int64_t image_elems, uint64_t seed,
+                             void* stream) {
+  if (!ctx || !mu || !out || B < 1 || image_elems < 1) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  if (!ctx->have_sched) return fail(ctx, IRSDE_ERR_STATE, "schedule not set");
+  cudaSetDevice(ctx->cfg.device);
+  if (ctx->n_uids && ctx->n_uids != B) return fail(ctx, IRSDE_ERR_INVALID, "irsde_set_image_uids count does not match the batch");
+  launch_noise_state(mu, out, (long long)B * image_elems, ctx->max_sigma, seed, image_elems, ctx->image_base,
+                     ctx->n_uids ? ctx->d_uids : nullptr, (cudaStream_t)stream);
+  ctx->launches++;
+  CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
+int irsde_set_image_base(irsde_ctx* ctx, uint64_t first_image_uid) {
+  if (!ctx) return fail(ctx, IRSDE_ERR_INVALID, "null ctx");
+  ctx->image_base = first_image_uid;
+  ctx->n_uids = 0;
+  return IRSDE_OK;
+}
+
+int irsde_set_image_uids(irsde_ctx* ctx, const uint64_t* uids, int32_t n, void* stream) {
+  const int MAX_UIDS = 4096;
+  if (!ctx || !uids || n < 1 || n > MAX_UIDS) return fail(ctx, IRSDE_ERR_INVALID, "uids: need 1..4096 host values");
+  cudaSetDevice(ctx->cfg.device);
+  if (!ctx->d_uids) {
+    ctx->d_uids = (unsigned long long*)dev_alloc(ctx, sizeof(unsigned long long) * MAX_UIDS, &ctx->allocs);
+    if (!ctx->d_uids) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+  }
+  // pageable host source: the copy is staged before the call returns, so the caller may reuse `uids` at once
+  CUDA_TRY(ctx, cudaMemcpyAsync(ctx->d_uids, uids, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  ctx->n_uids = n;
   return IRSDE_OK;
 }
 
@@ -1721,6 +1765,48 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
   }
   for (void* q : tmp) { cudaFree(q); }
   return rc;
+}
+
+// ---- image conversion / metrics (stateless) ----------------------------------------------------------------
+static int img_args_ok(const void* a, const void* b, int B, int C, int H, int W) {
+  if (!a || !b || B < 1 || H < 1 || W < 1 || (C != 1 && C != 3)) return fail(nullptr, IRSDE_ERR_INVALID, "bad image argument");
+  return IRSDE_OK;
+}
+static int img_launch_status(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, IRSDE_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+  return IRSDE_OK;
+}
+int irsde_tensor2img_u8(const float* chw, uint8_t* hwc, int32_t B, int32_t C, int32_t H, int32_t W, double lo, double hi,
+                        void* stream) {
+  if (int rc = img_args_ok(chw, hwc, B, C, H, W)) return rc;
+  if (!(hi > lo)) return fail(nullptr, IRSDE_ERR_INVALID, "min_max must be increasing");
+  launch_tensor2img(chw, hwc, B, C, H, W, lo, hi, (cudaStream_t)stream);
+  return img_launch_status("tensor2img");
+}
+int irsde_img2tensor_u8(const uint8_t* hwc, float* chw, int32_t B, int32_t C, int32_t H, int32_t W, void* stream) {
+  if (int rc = img_args_ok(hwc, chw, B, C, H, W)) return rc;
+  launch_img2tensor(hwc, chw, B, C, H, W, (cudaStream_t)stream);
+  return img_launch_status("img2tensor");
+}
+int irsde_sqerr_u8(const uint8_t* a, const uint8_t* b, int32_t B, int32_t H, int32_t W, int32_t C, int32_t crop, uint64_t* sums,
+                   void* stream) {
+  if (int rc = img_args_ok(a, b, B, C, H, W)) return rc;
+  if (!sums || crop < 0 || H - 2 * crop < 1 || W - 2 * crop < 1) return fail(nullptr, IRSDE_ERR_INVALID, "bad crop / output");
+  launch_sqerr_u8(a, b, B, H, W, C, crop, (unsigned long long*)sums, (cudaStream_t)stream);
+  return img_launch_status("sqerr_u8");
+}
+int64_t irsde_ssim_workspace(int32_t B, int32_t H, int32_t W, int32_t C, int32_t crop) {
+  if (B < 1 || crop < 0 || H - 2 * crop < 11 || W - 2 * crop < 11) return 0;
+  return (int64_t)B * ssim_partial_count(H, W, C, crop);
+}
+int irsde_ssim_u8(const uint8_t* a, const uint8_t* b, int32_t B, int32_t H, int32_t W, int32_t C, int32_t crop, double* workspace,
+                  double* ssim, void* stream) {
+  if (int rc = img_args_ok(a, b, B, C, H, W)) return rc;
+  if (!workspace || !ssim || crop < 0 || H - 2 * crop < 11 || W - 2 * crop < 11)
+    return fail(nullptr, IRSDE_ERR_INVALID, "SSIM needs at least 11x11 pixels after cropping");
+  launch_ssim_u8(a, b, B, H, W, C, crop, workspace, ssim, (cudaStream_t)stream);
+  return img_launch_status("ssim_u8");
 }
 
 }  // extern "C"

@@ -63,10 +63,12 @@ __global__ void __launch_bounds__(256) dwgate_kernel(const T* __restrict__ x, in
 // mean over pixels -> 1x1 conv (c x c mat-vec + bias): sca[b][o]            (DenoisingNAFNet_arch.py:29-33)
 // grid (ceil(c/8), B): every block re-derives the c means (c*nchunks floats, L2 resident) and its 8 warps each own
 // one output row, so the c x c weight matrix is streamed by c/8 SMs instead of one.
+template <typename T>
 __global__ void __launch_bounds__(256) sca_kernel(const float* __restrict__ partial, const float* __restrict__ w,
                                                   const float* __restrict__ bias, float* __restrict__ sca, int c, int nchunks,
-                                                  int N) {
+                                                  int N, T* __restrict__ g, int g_pitch) {
   extern __shared__ float mean_s[];
+  __shared__ float row_s[8];
   const int b = blockIdx.y;
   for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
     float s = 0.f;
@@ -76,12 +78,21 @@ __global__ void __launch_bounds__(256) sca_kernel(const float* __restrict__ part
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int o = blockIdx.x * 8 + warp;
-  if (o >= c) return;
-  float s = 0.f;
-  for (int k = lane; k < c; k += 32) s += w[(long long)o * c + k] * mean_s[k];
+  if (o < c) {
+    float s = 0.f;
+    for (int k = lane; k < c; k += 32) s += w[(long long)o * c + k] * mean_s[k];
 #pragma unroll
-  for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-  if (lane == 0) sca[(long long)b * c + o] = s + bias[o];
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if (lane == 0) { s += bias[o]; sca[(long long)b * c + o] = s; row_s[warp] = s; }
+  }
+  if (g == nullptr) return;
+  // small images: scale this block's 8 channels of the gate tensor in place (the "x * self.sca(x)" of :67)
+  __syncthreads();
+  const int nch = min(8, c - blockIdx.x * 8);
+  for (int p = threadIdx.x; p < N; p += blockDim.x) {
+    T* e = g + ((long long)b * N + p) * g_pitch + blockIdx.x * 8;
+    for (int j = 0; j < nch; ++j) e[j] = from_f<T>(to_f(e[j]) * row_s[j]);
+  }
 }
 
 // x[b,p,ch] *= sca[b][ch]   (in place; the "x * self.sca(x)" of :67)
@@ -154,9 +165,21 @@ void launch_dwgate(const T* x, int x_pitch, const float* w, const float* bias, T
 template void launch_dwgate<float>(const float*, int, const float*, const float*, float*, int, float*, int, int, int, int, cudaStream_t);
 template void launch_dwgate<bf16>(const bf16*, int, const float*, const float*, bf16*, int, float*, int, int, int, int, cudaStream_t);
 
-void launch_sca(const float* partial, const float* w, const float* bias, float* sca, int B, int c, int nchunks, int N, cudaStream_t st) {
-  sca_kernel<<<dim3((c + 7) / 8, B), 256, c * sizeof(float), st>>>(partial, w, bias, sca, c, nchunks, N);
+template <typename T>
+void launch_scale_channels(T* x, int pitch, const float* sca, int B, int N, int c, cudaStream_t st);
+
+// sca[b][:] and g *= sca in place.  N <= 1024 pixels: one launch does both; larger images use a second, fully
+// parallel pass (8 channels per block would not cover the pixels fast enough).
+template <typename T>
+void launch_sca_scale(const float* partial, const float* w, const float* bias, float* sca, T* g, int g_pitch, int B, int c,
+                      int nchunks, int N, int* launches, cudaStream_t st) {
+  const bool fused = N <= 1024;
+  sca_kernel<T><<<dim3((c + 7) / 8, B), 256, c * sizeof(float), st>>>(partial, w, bias, sca, c, nchunks, N, fused ? g : (T*)nullptr, g_pitch);
+  *launches = 1;
+  if (!fused) { launch_scale_channels<T>(g, g_pitch, sca, B, N, c, st); *launches = 2; }
 }
+template void launch_sca_scale<float>(const float*, const float*, const float*, float*, float*, int, int, int, int, int, int*, cudaStream_t);
+template void launch_sca_scale<bf16>(const float*, const float*, const float*, float*, bf16*, int, int, int, int, int, int*, cudaStream_t);
 
 template <typename T>
 void launch_scale_channels(T* x, int pitch, const float* sca, int B, int N, int c, cudaStream_t st) {

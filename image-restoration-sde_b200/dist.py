@@ -31,19 +31,29 @@ def broadcast_weights(model, src=0):
     return flat.numel()
 
 
-def sharded_reverse(run, xT, mu=None, zs=None, group=None, gather=True):
+def sharded_reverse(run, xT, mu=None, zs=None, group=None, gather=True, sde=None):
     """Run ``run(xT_slice, mu_slice, zs_slice)`` on this rank's slice of the batch and gather x0.
 
     ``run`` is e.g. ``lambda x, m, z: (sde.set_mu(m), sde.reverse_sde(x, zs=z))[1]``.  ``zs`` is
     [T,B,...] drawn for the FULL batch, so that every image sees the same noise regardless of the
-    number of ranks (bit-identical to the single-GPU result).  Returns the full [B,...] tensor on
+    number of ranks (bit-identical to the single-GPU result).  With the in-kernel Philox (``zs`` None,
+    ``sde.rng == "philox"``) pass ``sde``: its ``image_base`` is moved to this rank's first image for the call, which
+    gives the same bit-identical guarantee without materialising any noise.  Returns the full [B,...] tensor on
     every rank (all_gather), or the local slice if ``gather`` is False.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     B = xT.shape[0]
     lo, hi = shard_range(B, rank, world)
-    out = run(xT[lo:hi], None if mu is None else mu[lo:hi], None if zs is None else zs[:, lo:hi])
+    base = None
+    if sde is not None:
+        base = sde.image_base
+        sde.image_base = base + lo
+    try:
+        out = run(xT[lo:hi], None if mu is None else mu[lo:hi], None if zs is None else zs[:, lo:hi])
+    finally:
+        if sde is not None:
+            sde.image_base = base
     if not gather or world == 1:
         return out
     sizes = [shard_range(B, r, world) for r in range(world)]

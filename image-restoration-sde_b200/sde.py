@@ -59,6 +59,9 @@ class _SDEBase:
         self.use_graph = os.environ.get("IRSDE_B200_GRAPH", "1") != "0"
         self.rng = os.environ.get("IRSDE_B200_RNG", "torch")  # "torch": randn_like per step; "philox": in-kernel
         self.seed = 0
+        self.seed_auto_increment = True   # a fresh Philox seed per chain; False: (seed, image uid, t) fully decide the noise
+        self.image_base = 0               # uid of the first image of the next batch (Philox is keyed per image)
+        self.image_uids = None            # or explicit uids, one per image of the next batch
 
     # ---- per-timestep scalars in the reference's op order (0-dim fp32 tensor math) ----------------
     def _coeff_table(self, mode):
@@ -123,6 +126,16 @@ class _SDEBase:
         self._upload_schedule(ctx)
         return ctx
 
+    def _apply_image_ids(self, ctx, B, st):
+        if self.image_uids is not None:
+            u = [int(v) for v in self.image_uids]
+            if len(u) != B:
+                raise ValueError("image_uids must hold one uid per image of the batch")
+            arr = (ctypes.c_uint64 * B)(*u)
+            _lib.check(ctx.L.irsde_set_image_uids(ctx.h, arr, B, ctypes.c_void_p(st)), ctx.h)
+        else:
+            _lib.check(ctx.L.irsde_set_image_base(ctx.h, int(self.image_base)), ctx.h)
+
     def _native_step(self, mode, x, mu, noise, z, t):
         ctx = self._ctx_for(x)
         x = x.contiguous().float()
@@ -159,9 +172,11 @@ class _SDEBase:
         p = lambda a: ctypes.c_void_p(a.data_ptr()) if a is not None else None
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream().cuda_stream
+            self._apply_image_ids(ctx, B, st)
             _lib.check(ctx.L.irsde_reverse(ctx.h, mode, p(x), p(mu), p(zs), p(out), B, H, W, int(T), int(self.seed),
                                            1 if self.use_graph else 0, ctypes.c_void_p(st)), ctx.h)
-        self.seed += 1
+        if self.seed_auto_increment:
+            self.seed += 1
         self._keep = (x, mu, zs)  # keep inputs alive until the stream consumed them
         return out
 
@@ -291,7 +306,19 @@ class IRSDE(_SDEBase):
 
     def noise_state(self, tensor):
         # called on CPU tensors by test.py:104 before feed_data: plain torch, like the reference
-        return tensor + torch.randn_like(tensor) * self.max_sigma
+        if not (tensor.is_cuda and self.rng == "philox"):
+            return tensor + torch.randn_like(tensor) * self.max_sigma
+        # device path: x_T drawn by the library's per-image Philox, nothing crosses PCIe
+        ctx = self._ctx_for(tensor)
+        mu = tensor.contiguous().float()
+        out = torch.empty_like(mu)
+        B = mu.shape[0] if mu.dim() == 4 else 1
+        with torch.cuda.device(mu.device):
+            st = torch.cuda.current_stream().cuda_stream
+            self._apply_image_ids(ctx, B, st)
+            _lib.check(ctx.L.irsde_noise_state_images(ctx.h, ctypes.c_void_p(mu.data_ptr()), ctypes.c_void_p(out.data_ptr()), B,
+                                                      mu.numel() // B, int(self.seed), ctypes.c_void_p(st)), ctx.h)
+        return out
 
 
 class DenoisingSDE(_SDEBase):

@@ -143,8 +143,21 @@ int irsde_step(irsde_ctx* ctx, int32_t mode, const float* x, const float* mu, co
 int irsde_reverse(irsde_ctx* ctx, int32_t mode, const float* xT, const float* mu, const float* z, float* x0,
                   int32_t B, int32_t H, int32_t W, int32_t T, uint64_t seed, int32_t use_graph, void* stream);
 
-/* x_T = mu + N(0,1)*max_sigma on the device (sde_utils.py:360-361) with the library's Philox. */
+/* x_T = mu + N(0,1)*max_sigma on the device (sde_utils.py:360-361) with the library's Philox; the n floats are
+ * treated as ONE image (uid = the ctx's image base). */
 int irsde_noise_state(irsde_ctx* ctx, const float* mu, float* out, int64_t n, uint64_t seed, void* stream);
+/* Same for a batch [B][image_elems]: image b is drawn with uid = image base + b. */
+int irsde_noise_state_images(irsde_ctx* ctx, const float* mu, float* out, int32_t B, int64_t image_elems, uint64_t seed,
+                             void* stream);
+/* The in-kernel Philox (irsde_reverse with z == NULL, irsde_noise_state*) is keyed by
+ * (seed, image uid, timestep, element index inside the image), uid = image base + position in the batch.
+ * An image's noise therefore does not depend on the batch it is processed in, its position, or the rank that
+ * owns it: set the base to the global index of the shard's / batch's first image (default 0) and batched,
+ * sharded and one-at-a-time runs give bit-identical images (SURVEY.md 8 a-16 xi, e, f-2). */
+int irsde_set_image_base(irsde_ctx* ctx, uint64_t first_image_uid);
+/* Explicit uids for the next batch (n host values, n == B of the following calls), e.g. when a batch is assembled from
+ * same-sized images that are not consecutive in the dataset.  irsde_set_image_base() returns to base + position. */
+int irsde_set_image_uids(irsde_ctx* ctx, const uint64_t* uids, int32_t n, void* stream);
 
 /* Instrumented pass: between begin/end every op of the launch plan is bracketed by CUDA events on the
  * launching stream (graph replay is bypassed).  end() synchronises and returns, per op category
@@ -166,6 +179,23 @@ int64_t irsde_device_bytes(const irsde_ctx* ctx);
 int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w, const float* bias, float* y,
                  int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
                  int32_t pad, int32_t upsample, int32_t silu, void* stream);
+
+/* ---- image conversion and full-reference metrics on the device -------------------
+ * Stateless (no ctx): errors are reported through the return code and irsde_last_error(NULL).
+ * Replaces util.tensor2img (codes/utils/img_utils.py:136-163), img2tensor / read_img's "/255." (:171-180,
+ * codes/data/util.py:72), calculate_psnr (:182-190) and ssim / calculate_ssim (:193-234).  All pointers are
+ * device pointers.  Images are uint8 [B][H][W][C] (BGR when C == 3, the cv2 order), tensors fp32 [B][C][H][W] RGB. */
+int irsde_tensor2img_u8(const float* chw, uint8_t* hwc, int32_t B, int32_t C, int32_t H, int32_t W, double lo, double hi,
+                        void* stream);
+int irsde_img2tensor_u8(const uint8_t* hwc, float* chw, int32_t B, int32_t C, int32_t H, int32_t W, void* stream);
+/* sums[b] = sum over the crop-bordered region of (a - b)^2, exact; PSNR = 20 log10(255 / sqrt(sums / n)). */
+int irsde_sqerr_u8(const uint8_t* a, const uint8_t* b, int32_t B, int32_t H, int32_t W, int32_t C, int32_t crop,
+                   uint64_t* sums, void* stream);
+/* number of doubles irsde_ssim_u8 needs as workspace */
+int64_t irsde_ssim_workspace(int32_t B, int32_t H, int32_t W, int32_t C, int32_t crop);
+/* ssim[b] = mean SSIM of the crop-bordered images (11x11 Gaussian window, valid region), fp64 */
+int irsde_ssim_u8(const uint8_t* a, const uint8_t* b, int32_t B, int32_t H, int32_t W, int32_t C, int32_t crop,
+                  double* workspace, double* ssim, void* stream);
 
 #ifdef __cplusplus
 }

@@ -447,3 +447,117 @@ def test_latent_unet_bf16_and_real_architecture(lib):
         assert _maxdiff(z, zo) < tz, (prec, _maxdiff(z, zo))
         y = net.decode(zo.to(dev), h)
         assert _maxdiff(y, yo) < ty, (prec, _maxdiff(y, yo))
+
+
+# ------------------------------------------------------------------------------------------------
+# image helpers on the device: tensor2img / img2tensor / PSNR / SSIM
+# ------------------------------------------------------------------------------------------------
+def test_imaging_bit_exact_vs_reference(lib):
+    import os
+    import numpy as np
+    dev = _dev()
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_imaging.npz"))
+    for k in "abc":
+        t = torch.from_numpy(g["t_" + k]).to(dev)
+        assert np.array_equal(lib.tensor2img(t), g["img_" + k])                    # uint8, BGR/HWC, .5 ties: bit exact
+        assert np.array_equal(lib.tensor2img(t * 2 - 1, min_max=(-1, 1)), g["img11_" + k])
+    x, y = g["x"], g["y"]
+    assert np.array_equal(lib.imaging.img2tensor_device(x).cpu().numpy(), g["x_tensor"])
+    assert lib.calculate_psnr(x, y) == float(g["psnr"])                            # exact integer sum -> same float64
+    assert lib.calculate_psnr(x, y, crop_border=4) == float(g["psnr_crop4"])
+    assert lib.calculate_psnr(x, x) == float("inf")
+    assert abs(lib.calculate_ssim(x, y) - float(g["ssim"])) < 1e-10
+    assert abs(lib.calculate_ssim(x, y, crop_border=4) - float(g["ssim_crop4"])) < 1e-10
+    assert abs(lib.calculate_ssim(x[:, :, 0], y[:, :, 0]) - float(g["ssim_gray"])) < 1e-10
+    with pytest.raises(ValueError):
+        lib.calculate_ssim(x[:12, :12], y[:12, :12], crop_border=1)               # 10x10 after crop: no valid window
+
+
+def test_imaging_batched_vs_oracle(lib):
+    """Batch of 256x256 images (vectorised path) and a ragged 321x481 one: device == numpy oracle, bit for bit."""
+    import numpy as np
+    from oracle import imaging_oracle as IO
+    dev = _dev()
+    g = torch.Generator().manual_seed(5)
+    t = torch.rand(4, 3, 256, 256, generator=g) * 1.2 - 0.1
+    imgs = lib.imaging.tensor2img_device(t.to(dev))
+    ref = np.stack([IO.tensor2img(t[i].numpy()) for i in range(4)])
+    assert imgs.dtype == torch.uint8 and np.array_equal(imgs.cpu().numpy(), ref)
+    back = lib.imaging.img2tensor_device(imgs)
+    assert np.array_equal(back.cpu().numpy(), np.stack([IO.img2tensor(ref[i]) for i in range(4)]))
+    other = torch.from_numpy(ref).roll(1, 0)
+    se = lib.imaging.sqerr_device(imgs, other.to(dev), crop_border=3).cpu().numpy()
+    for i in range(4):
+        a, b = ref[i][3:-3, 3:-3].astype(np.int64), other[i].numpy()[3:-3, 3:-3].astype(np.int64)
+        assert int(se[i]) == int(((a - b) ** 2).sum())
+    noisy = np.clip(ref.astype(np.int32) + torch.randint(-9, 10, ref.shape, generator=g).numpy(), 0, 255).astype(np.uint8)
+    ss = lib.imaging.ssim_device(ref, noisy).cpu().numpy()
+    for i in range(4):
+        assert abs(ss[i] - IO.calculate_ssim(ref[i], noisy[i])) < 1e-10
+    r = torch.rand(3, 321, 481, generator=g)
+    assert np.array_equal(lib.tensor2img(r.to(dev)), IO.tensor2img(r.numpy()))
+
+
+# ------------------------------------------------------------------------------------------------
+# per-image Philox + batched restoration front-end (SURVEY 8 f-2)
+# ------------------------------------------------------------------------------------------------
+def test_philox_is_keyed_per_image(lib):
+    """In-kernel noise depends on (seed, image uid, t, element) only: batched == sharded == one at a time, bit for bit,
+    also when an image's element count is not a multiple of 4 (Philox blocks straddle images)."""
+    dev = _dev()
+    torch.manual_seed(0)
+    net = lib.ConditionalUNet(3, 3, 8, depth=2).to(dev)
+    sde = lib.IRSDE(25, 6, eps=0.005, device=dev)
+    sde.set_model(net)
+    sde.rng, sde.seed_auto_increment, sde.seed = "philox", False, 11
+    for (H, W) in ((12, 16), (9, 7)):            # 3*9*7 = 189 elements per image: not a multiple of 4
+        lq = torch.rand(4, 3, H, W, device=dev)
+        sde.image_base, sde.image_uids = 0, None
+        xT = sde.noise_state(lq)
+        sde.set_mu(lq)
+        full = sde.reverse_sde(xT)
+        assert (xT - lq).std().item() > 0.5 * sde.max_sigma
+        assert not torch.equal(xT[0] - lq[0], xT[1] - lq[1])                       # images get different noise
+        for lo, hi in ((0, 2), (2, 4), (1, 2), (3, 4)):
+            sde.image_base = lo
+            assert torch.equal(sde.noise_state(lq[lo:hi]), xT[lo:hi])
+            sde.set_mu(lq[lo:hi])
+            assert torch.equal(sde.reverse_sde(xT[lo:hi]), full[lo:hi])
+        sde.image_base, sde.image_uids = 0, [3, 1]                                  # explicit uids: a re-ordered batch
+        sel = torch.tensor([3, 1], device=dev)
+        assert torch.equal(sde.noise_state(lq[sel]), xT[sel])
+        sde.set_mu(lq[sel])
+        assert torch.equal(sde.reverse_sde(xT[sel]), full[sel])
+        sde.image_uids = None
+    sde.seed = 12
+    assert not torch.equal(sde.noise_state(lq), xT)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_restorer_batched_equals_single(lib, precision):
+    """uint8 in -> uint8 out; mixed image sizes; any batch size gives the images of the one-at-a-time run, and those
+    equal the hand-written sequence img2tensor -> noise_state -> reverse_sde -> tensor2img."""
+    import numpy as np
+    dev = _dev()
+    torch.manual_seed(1)
+    net = lib.ConditionalUNet(3, 3, 16, depth=2, precision=precision).to(dev)
+    sde = lib.IRSDE(10, 5, eps=0.005, device=dev)
+    sde.set_model(net)
+    g = torch.Generator().manual_seed(2)
+    shapes = [(24, 32), (16, 16), (24, 32), (24, 32), (16, 16), (24, 32)]
+    imgs = [(torch.rand(h, w, 3, generator=g) * 255).to(torch.uint8).numpy() for h, w in shapes]
+    one = lib.Restorer(sde, mode="sde", batch_size=1, seed=5).restore(imgs)
+    for bs in (2, 4):
+        many = lib.Restorer(sde, mode="sde", batch_size=bs, seed=5).restore(imgs)
+        for a, b in zip(one, many):
+            assert a.dtype == np.uint8 and a.shape == b.shape and np.array_equal(a, b)
+    assert not np.array_equal(one[0], lib.Restorer(sde, mode="sde", batch_size=4, seed=6).restore(imgs)[0])
+    # image 4 by hand
+    sde.rng, sde.seed, sde.seed_auto_increment, sde.image_uids = "philox", 5, False, [4]
+    lq = lib.imaging.img2tensor_device(imgs[4])[None]
+    sde.set_mu(lq)
+    x0 = sde.reverse_sde(sde.noise_state(lq))
+    assert np.array_equal(lib.tensor2img(x0), one[4])
+    sde.image_uids = None
+    assert np.array_equal(lib.Restorer(sde, mode="ode", batch_size=3).restore(imgs)[2],
+                          lib.Restorer(sde, mode="ode", batch_size=1).restore(imgs)[2])

@@ -147,3 +147,15 @@ def test_launcher_patches_reference_tree():
         "assert isinstance(naf, irsde_b200.ConditionalNAFNet); print('ok')" % (ROOT, ref, ref))
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_plan_batches_groups_by_shape():
+    import irsde_b200
+    shapes = [(4, 4, 3), (8, 8, 3), (4, 4, 3), (4, 4, 3), (8, 8, 3), (4, 4, 3)]
+    plan = irsde_b200.plan_batches(shapes, 2)
+    assert plan == [((4, 4, 3), [0, 2]), ((4, 4, 3), [3, 5]), ((8, 8, 3), [1, 4])]
+    assert sorted(i for _, idx in plan for i in idx) == list(range(6))           # every image exactly once
+    assert irsde_b200.plan_batches([], 4) == []
+    import pytest
+    with pytest.raises(ValueError):
+        irsde_b200.plan_batches(shapes, 0)

@@ -150,3 +150,28 @@ def test_latent_unet_oracle_real_checkpoint():
     # the well-conditioned random-weight fixture (test_latent_unet_oracle_vs_reference).
     assert y.shape == x.shape
     assert list(O.latent_unet_param_shapes(3, 3, 8, [4, 8, 8, 16], 8)) == list(sd)
+
+
+# ---- image helpers (oracle/imaging_oracle.py vs the reference's img_utils outputs) ---------------------------
+def _imaging_golden():
+    import os
+    import numpy as np
+    return np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_imaging.npz"))
+
+
+def test_imaging_oracle_matches_reference():
+    import numpy as np
+    from oracle import imaging_oracle as IO
+    g = _imaging_golden()
+    for k in "abc":
+        t = g["t_" + k]
+        t2 = t[0] if t.shape[0] == 1 else t
+        assert np.array_equal(IO.tensor2img(t2), g["img_" + k])                              # bit exact, incl. .5 ties
+        assert np.array_equal(IO.tensor2img(t2 * np.float32(2) - np.float32(1), (-1, 1)), g["img11_" + k])
+    assert np.array_equal(IO.img2tensor(g["x"]), g["x_tensor"])
+    assert IO.calculate_psnr(g["x"], g["y"]) == float(g["psnr"])                            # exact integer sums
+    assert IO.calculate_psnr(g["x"][4:-4, 4:-4], g["y"][4:-4, 4:-4]) == float(g["psnr_crop4"])
+    assert IO.calculate_psnr(g["x"], g["x"]) == float("inf")
+    assert abs(IO.calculate_ssim(g["x"], g["y"]) - float(g["ssim"])) < 1e-12
+    assert abs(IO.calculate_ssim(g["x"][4:-4, 4:-4], g["y"][4:-4, 4:-4]) - float(g["ssim_crop4"])) < 1e-12
+    assert abs(IO.calculate_ssim(g["x"][:, :, 0], g["y"][:, :, 0]) - float(g["ssim_gray"])) < 1e-12
