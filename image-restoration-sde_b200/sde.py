@@ -289,6 +289,51 @@ class IRSDE(_SDEBase):
     def reverse_sde_step_mean(self, x, score, t):
         return x - (self.thetas[t] * (self.mu - x) - self.sigmas[t] ** 2 * score) * self.dt
 
+    # forward-process / diagnostic helpers of the reference (sde_utils.py:39-52,170-182,207-217,240-251,326-333); not on the
+    # sampling hot path, plain tensor algebra on whatever device the inputs live on
+    def drift(self, x, t):
+        return self.thetas[t] * (self.mu - x) * self.dt
+
+    def dispersion(self, x, t):
+        return self.sigmas[t] * (torch.randn_like(x) * math.sqrt(self.dt)).to(self.device)
+
+    def sde_reverse_drift(self, x, score, t):
+        return (self.thetas[t] * (self.mu - x) - self.sigmas[t] ** 2 * score) * self.dt
+
+    def ode_reverse_drift(self, x, score, t):
+        return (self.thetas[t] * (self.mu - x) - 0.5 * self.sigmas[t] ** 2 * score) * self.dt
+
+    def forward_step(self, x, t):
+        return x + self.drift(x, t) + self.dispersion(x, t)
+
+    def forward(self, x0, T=-1, save_dir=None):
+        """x(0) -> x(T) by Euler-Maruyama steps of the forward SDE (the reference also dumps every state as a PNG into
+        ``save_dir='forward_state'``; here only when a directory is given)."""
+        T = self.T if T < 0 else T
+        x = x0.clone()
+        for t in range(1, T + 1):
+            x = self.forward_step(x, t)
+            if save_dir:
+                import torchvision.utils as tvutils
+                os.makedirs(save_dir, exist_ok=True)
+                tvutils.save_image(x.data, f"{save_dir}/state_{t}.png", normalize=False)
+        return x
+
+    def reverse_optimum_std(self, t):
+        A = torch.exp(-2 * self.thetas[t] * self.dt)
+        B = torch.exp(-2 * self.thetas_cumsum[t] * self.dt)
+        C = torch.exp(-2 * self.thetas_cumsum[t - 1] * self.dt)
+        var = (1 - A) * (1 - C) / (1 - B)
+        floor = (1e-20 * self.dt).to(self.device)
+        return (0.5 * torch.log(torch.clamp(var, min=floor))).exp() * self.max_sigma
+
+    def optimal_reverse(self, xt, x0, T=-1):
+        T = self.T if T < 0 else T
+        x = xt.clone()
+        for t in reversed(range(1, T + 1)):
+            x = self.reverse_optimum_step(x, x0, t)
+        return x
+
     def weights(self, t):
         return torch.exp(-self.thetas_cumsum[t] * self.dt)
 
@@ -393,6 +438,31 @@ class DenoisingSDE(_SDEBase):
 
     def reverse_ode(self, xt, x0=None, T=-1, save_states=False, save_dir="ode_state", zs=None):
         return self._loop(_lib.MODE_DSDE_ODE, xt, x0, T, save_states, save_dir, zs)
+
+    # reference helpers off the sampling path (sde_utils.py:446-459,556-571): plain tensor algebra
+    def drift(self, x, x0, t):
+        return self.thetas[t] * (x0 - x) * self.dt
+
+    def sde_reverse_drift(self, x, score, t):
+        A = torch.exp(-2 * self.thetas_cumsum[t] * self.dt)
+        return -0.5 * self.sigmas[t] ** 2 * (1 + A) * score * self.dt
+
+    def ode_reverse_drift(self, x, score, t):
+        A = torch.exp(-2 * self.thetas_cumsum[t] * self.dt)
+        return -0.5 * self.sigmas[t] ** 2 * A * score * self.dt
+
+    def dispersion(self, x, t):
+        return self.sigmas[t] * (torch.randn_like(x) * math.sqrt(self.dt)).to(self.device)
+
+    def reverse_sde_step_mean(self, x, score, t):
+        return x - self.sde_reverse_drift(x, score, t)
+
+    def optimal_reverse(self, xt, x0, T=-1):
+        T = self.T if T < 0 else T
+        x = xt.clone()
+        for t in reversed(range(1, T + 1)):
+            x = self.reverse_optimum_step(x, x0, t)
+        return x
 
     def get_optimal_timestep(self, sigma, eps=1e-6):
         sigma = sigma / 255 if sigma > 1 else sigma

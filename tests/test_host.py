@@ -159,3 +159,39 @@ def test_plan_batches_groups_by_shape():
     import pytest
     with pytest.raises(ValueError):
         irsde_b200.plan_batches(shapes, 0)
+
+
+def test_sde_diagnostic_helpers_match_reference_algebra():
+    """drift / reverse drifts / reverse_optimum_std / forward_step: the reference's formulas (sde_utils.py:170-182,207-217,
+    446-456) evaluated on CPU tensors - these helpers are plain tensor algebra and need no GPU."""
+    import math
+    import torch
+    import irsde_b200
+    sde = irsde_b200.IRSDE(max_sigma=30, T=20, schedule="cosine", eps=0.005, device="cpu")
+    g = torch.Generator().manual_seed(0)
+    x, mu, sc = (torch.randn(2, 3, 4, 4, generator=g) for _ in range(3))
+    sde.set_mu(mu)
+    t = 7
+    th, sg, dt = sde.thetas[t], sde.sigmas[t], sde.dt
+    assert torch.equal(sde.drift(x, t), th * (mu - x) * dt)
+    assert torch.equal(sde.sde_reverse_drift(x, sc, t), (th * (mu - x) - sg ** 2 * sc) * dt)
+    assert torch.equal(sde.ode_reverse_drift(x, sc, t), (th * (mu - x) - 0.5 * sg ** 2 * sc) * dt)
+    assert torch.equal(sde.reverse_sde_step_mean(x, sc, t), x - sde.sde_reverse_drift(x, sc, t))
+    torch.manual_seed(3)
+    d = sde.dispersion(x, t)
+    torch.manual_seed(3)
+    assert torch.equal(d, sg * (torch.randn_like(x) * math.sqrt(dt)))
+    # posterior std equals the closed form and collapses at t = 1 (deterministic last step, SURVEY 8 a-6)
+    A, B, C = (torch.exp(-2 * v * dt) for v in (sde.thetas[t], sde.thetas_cumsum[t], sde.thetas_cumsum[t - 1]))
+    assert abs(sde.reverse_optimum_std(t).item() - (((1 - A) * (1 - C) / (1 - B)).sqrt() * sde.max_sigma).item()) < 1e-7
+    assert sde.reverse_optimum_std(1).item() < 1e-9
+    # optimal_reverse with the true x0 walks back to x0
+    x0 = torch.rand(1, 3, 4, 4, generator=g)
+    sde.set_mu(torch.rand(1, 3, 4, 4, generator=g))
+    xT = sde.mu_bar(x0, sde.T)
+    assert (sde.optimal_reverse(xT, x0) - x0).abs().max().item() < 1e-3
+    ds = irsde_b200.DenoisingSDE(max_sigma=50, T=20, device="cpu")
+    Ad = torch.exp(-2 * ds.thetas_cumsum[t] * ds.dt)
+    assert torch.equal(ds.sde_reverse_drift(x, sc, t), -0.5 * ds.sigmas[t] ** 2 * (1 + Ad) * sc * ds.dt)
+    assert torch.equal(ds.ode_reverse_drift(x, sc, t), -0.5 * ds.sigmas[t] ** 2 * Ad * sc * ds.dt)
+    assert torch.equal(ds.drift(x, mu, t), ds.thetas[t] * (mu - x) * ds.dt)
