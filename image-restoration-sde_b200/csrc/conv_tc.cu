@@ -679,11 +679,15 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     const bool affine = (P.ss != nullptr) || (P.bias != nullptr) || (P.mult_vec != nullptr);
     uint8_t* stg = smem_stg + (warp - 2) * 2048;
     long long w_tfull = 0, t_start = clock64();
-    int lt = 0;
+    int lt = 0, epi_n0 = -1, epi_b = -1;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const TileCoord t = decode_tile(P, tile, tiles_m, BN);
       const int acc = lt & 1;
-      if (affine) {
+      // The per-channel (mult, add) table depends on the N tile (and on the image only with per-image timesteps):
+      // rebuild it - two barriers and a dependent global load on the epilogue's critical path - only when that changes.
+      const int key_b = P.ss_img_stride ? t.b : 0;
+      if (affine && (t.n0 != epi_n0 || key_b != epi_b)) {
+        epi_n0 = t.n0; epi_b = key_b;
         asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's reads of s_epi are done
         const float* ssrow = P.ss ? P.ss + (long long)(trow + t.b * P.ss_img_stride) * P.ss_S + P.ss_off : nullptr;
         for (int j = et; j < BN; j += 256) {
