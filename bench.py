@@ -186,6 +186,7 @@ def run_b200(args):
     sde = irsde_b200.IRSDE(ms, T, schedule="cosine", eps=eps, device=dev)
     sde.set_model(net)
     sde.use_graph = not args.no_graph
+    sde.image_base = rank * B   # per-image Philox: rank r owns the global images [r*B, (r+1)*B)
 
     lq_cpu, g = synth(B, H, W, seed=1234 + rank)
     xT_cpu = lq_cpu + torch.randn(lq_cpu.shape, generator=g) * sde.max_sigma

@@ -1,7 +1,7 @@
 #!/bin/bash
 # same-box A/B of two libraries: altlib/libirsde_base.so vs the in-tree build (bench breakdown + a few bf16 tests)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests -q -m gpu -k "bf16 or tcgen05" -x -p no:cacheprovider 2>&1 | tail -3
+timeout 300 python -m pytest tests -q -m gpu -k "bf16 or tcgen05 or unet_forward or nafnet or chain" -x -p no:cacheprovider 2>&1 | tail -3
 run() { # name lib
   env IRSDE_B200_LIB=$PWD/$2 timeout 600 python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ab_$1.log 2>&1
   python - "$1" <<'PY'
