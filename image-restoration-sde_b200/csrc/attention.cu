@@ -58,6 +58,7 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict_
                                                             const float* __restrict__ g, const T* __restrict__ res,
                                                             int res_pitch, T* __restrict__ out, int out_pitch,
                                                             long long npix, int C, int lpp, LnMod mod) {
+  PDL_ENTRY();
   constexpr int N = VecIO<T>::N;
   const int lane = threadIdx.x & 31;
   const int ppw = 32 / lpp;
@@ -128,6 +129,7 @@ template <typename T>
 __global__ void layernorm_scalar_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
                                         const T* __restrict__ res, int res_pitch, T* __restrict__ out, int out_pitch,
                                         long long npix, int C, LnMod mod) {
+  PDL_ENTRY();
   int lane = threadIdx.x & 31;
   long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= npix) return;
@@ -171,7 +173,7 @@ void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int
   int per_lane = vec_ok ? (nvec + lpp - 1) / lpp : 999;
   if (!vec_ok || per_lane > 16) {
     const int warps = 8;
-    layernorm_scalar_kernel<T><<<(unsigned)((npix + warps - 1) / warps), warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch,
+    pdl_launch(layernorm_scalar_kernel<T>, (unsigned)((npix + warps - 1) / warps), warps * 32, 0, st, x, x_pitch, g, res, res_pitch,
                                                                                             out, out_pitch, npix, C, mod);
     return;
   }
@@ -179,7 +181,7 @@ void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int
   long long pix_per_block = (long long)warps * (32 / lpp);
   unsigned grid = (unsigned)((npix + pix_per_block - 1) / pix_per_block);
 #define LN_LAUNCH(MV) \
-  layernorm_vec_kernel<T, MV><<<grid, warps * 32, 0, st>>>(x, x_pitch, g, res, res_pitch, out, out_pitch, npix, C, lpp, mod)
+  pdl_launch(layernorm_vec_kernel<T, MV>, grid, warps * 32, 0, st, x, x_pitch, g, res, res_pitch, out, out_pitch, npix, C, lpp, mod)
   if (per_lane <= 1) LN_LAUNCH(1);
   else if (per_lane <= 2) LN_LAUNCH(2);
   else if (per_lane <= 4) LN_LAUNCH(4);
@@ -219,6 +221,7 @@ size_t linattn_partial_floats(int B, int N) { return (size_t)B * LA_MAXBLK * LA_
 template <typename T>
 __global__ void __launch_bounds__(256) la_kv_kernel(const T* __restrict__ qkv, int pitch, float* __restrict__ part,
                                                     int N, int nchunks, int nblk) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) float la_sm[];
   float (*ks)[128] = reinterpret_cast<float (*)[128]>(la_sm);               // [64][128] k -> p
   float (*vs)[128] = reinterpret_cast<float (*)[128]>(la_sm + LA_PIX * 128);  // [64][128]
@@ -310,6 +313,7 @@ __global__ void __launch_bounds__(256) la_kv_kernel(const T* __restrict__ qkv, i
 
 __global__ void __launch_bounds__(1024) la_combine_kernel(const float* __restrict__ part, float* __restrict__ ctx,
                                                           int N, int nblk) {
+  PDL_ENTRY();
   const int bh = blockIdx.x, b = bh >> 2, h = bh & 3, tid = threadIdx.x;
   const int d = tid >> 5;
   const float* base = part + (long long)b * LA_MAXBLK * LA_REC + h * 1088;
@@ -330,6 +334,7 @@ __global__ void __launch_bounds__(1024) la_combine_kernel(const float* __restric
 template <typename T>
 __global__ void __launch_bounds__(256) la_out_kernel(const T* __restrict__ qkv, int pitch, const float* __restrict__ ctx,
                                                      T* __restrict__ hidden, int hid_pitch, int N) {
+  PDL_ENTRY();
   __shared__ __align__(16) float cs[4][32][32];
   constexpr int NV = VecIO<T>::N;
   const int b = blockIdx.y, tid = threadIdx.x;
@@ -395,6 +400,7 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
 
 __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__ qkv, int pitch, float* __restrict__ part,
                                                         int N, int nchunks, int nblk) {
+  PDL_ENTRY();
   extern __shared__ __align__(16) uint8_t lam_sm[];
   bf16* tile = reinterpret_cast<bf16*>(lam_sm);                          // [2][64][LAM_TP]  (k | v)
   bf16* Ps = tile + 2 * LA_PIX * LAM_TP;                                 // [64][LAM_PP]
@@ -539,15 +545,15 @@ static void launch_la_kv(const T* qkv, int qkv_pitch, float* partial, int B, int
 template <>
 void launch_la_kv<float>(const float* qkv, int qkv_pitch, float* partial, int B, int N, int nchunks, int nblk, size_t smem,
                          cudaStream_t st) {
-  la_kv_kernel<float><<<dim3(nblk, B), 256, smem, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+  pdl_launch(la_kv_kernel<float>, dim3(nblk, B), 256, smem, st, qkv, qkv_pitch, partial, N, nchunks, nblk);
 }
 template <>
 void launch_la_kv<bf16>(const bf16* qkv, int qkv_pitch, float* partial, int B, int N, int nchunks, int nblk, size_t smem,
                         cudaStream_t st) {
   if (qkv_pitch % 8 == 0 && ((uintptr_t)qkv % 16) == 0)
-    la_kv_mma_kernel<<<dim3(nblk, B), 256, LAM_SMEM, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+    pdl_launch(la_kv_mma_kernel, dim3(nblk, B), 256, LAM_SMEM, st, qkv, qkv_pitch, partial, N, nchunks, nblk);
   else
-    la_kv_kernel<bf16><<<dim3(nblk, B), 256, smem, st>>>(qkv, qkv_pitch, partial, N, nchunks, nblk);
+    pdl_launch(la_kv_kernel<bf16>, dim3(nblk, B), 256, smem, st, qkv, qkv_pitch, partial, N, nchunks, nblk);
 }
 
 template <typename T>
@@ -562,7 +568,7 @@ void launch_linattn_ctx(const T* qkv, int qkv_pitch, float* partial, float* ctx,
     g_la_attr_done = true;
   }
   launch_la_kv<T>(qkv, qkv_pitch, partial, B, N, nchunks, nblk, smem, st);
-  la_combine_kernel<<<B * 4, 1024, 0, st>>>(partial, ctx, N, nblk);
+  pdl_launch(la_combine_kernel, B * 4, 1024, 0, st, partial, ctx, N, nblk);
 }
 template void launch_linattn_ctx<float>(const float*, int, float*, float*, int, int, cudaStream_t);
 template void launch_linattn_ctx<bf16>(const bf16*, int, float*, float*, int, int, cudaStream_t);
@@ -571,7 +577,7 @@ template <typename T>
 void launch_linattn(const T* qkv, int qkv_pitch, float* partial, float* ctx, T* hidden, int hid_pitch, int B, int N,
                     cudaStream_t st) {
   launch_linattn_ctx<T>(qkv, qkv_pitch, partial, ctx, B, N, st);
-  la_out_kernel<T><<<dim3((N + 63) / 64, B), 256, 0, st>>>(qkv, qkv_pitch, ctx, hidden, hid_pitch, N);
+  pdl_launch(la_out_kernel<T>, dim3((N + 63) / 64, B), 256, 0, st, qkv, qkv_pitch, ctx, hidden, hid_pitch, N);
 }
 template void launch_linattn<float>(const float*, int, float*, float*, float*, int, int, int, cudaStream_t);
 template void launch_linattn<bf16>(const bf16*, int, float*, float*, bf16*, int, int, int, cudaStream_t);
@@ -580,6 +586,7 @@ template void launch_linattn<bf16>(const bf16*, int, float*, float*, bf16*, int,
 // per-image-weight GEMM on the (head-softmaxed) q:  y[px][c] = sum_k qs[px][k] * Mb[b][c][k],
 // Mb[b][c][h*32+d] = sum_e Wout[c][h*32+e] * ctx[b][h][d][e]   (module_util.py:176-178 re-associated).
 __global__ void la_fold_kernel(const float* __restrict__ ctx, const float* __restrict__ wout, bf16* __restrict__ Mb, int C) {
+  PDL_ENTRY();
   __shared__ float cs[4][32][33];
   const int b = blockIdx.y;
   for (int i = threadIdx.x; i < 4096; i += blockDim.x) cs[i >> 10][(i >> 5) & 31][i & 31] = ctx[(long long)b * 4096 + i];
@@ -594,7 +601,7 @@ __global__ void la_fold_kernel(const float* __restrict__ ctx, const float* __res
   Mb[((long long)b * C + c) * 128 + k] = __float2bfloat16_rn(acc);
 }
 void launch_la_fold(const float* ctx, const float* wout, bf16* Mb, int B, int C, cudaStream_t st) {
-  la_fold_kernel<<<dim3((C + 1) / 2, B), 256, 0, st>>>(ctx, wout, Mb, C);
+  pdl_launch(la_fold_kernel, dim3((C + 1) / 2, B), 256, 0, st, ctx, wout, Mb, C);
 }
 
 // =============================================================================================
@@ -604,6 +611,7 @@ void launch_la_fold(const float* ctx, const float* wout, bf16* Mb, int B, int C,
 template <typename T>
 __global__ void __launch_bounds__(128) fullattn_kernel(const T* __restrict__ qkv, int pitch, T* __restrict__ hidden,
                                                        int hid_pitch, int N) {
+  PDL_ENTRY();
   __shared__ __align__(16) float ks[64][32];
   __shared__ __align__(16) float vs[64][32];
   int bh = blockIdx.y, b = bh >> 2, h = bh & 3;
@@ -668,7 +676,7 @@ __global__ void __launch_bounds__(128) fullattn_kernel(const T* __restrict__ qkv
 }
 template <typename T>
 void launch_fullattn(const T* qkv, int qkv_pitch, T* hidden, int hid_pitch, int B, int N, cudaStream_t st) {
-  fullattn_kernel<T><<<dim3((N + 127) / 128, B * 4), 128, 0, st>>>(qkv, qkv_pitch, hidden, hid_pitch, N);
+  pdl_launch(fullattn_kernel<T>, dim3((N + 127) / 128, B * 4), 128, 0, st, qkv, qkv_pitch, hidden, hid_pitch, N);
 }
 template void launch_fullattn<float>(const float*, int, float*, int, int, int, cudaStream_t);
 template void launch_fullattn<bf16>(const bf16*, int, bf16*, int, int, int, cudaStream_t);

@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(ConvGeom g, const T* __r
                                                         const float* __restrict__ w, Epilogue ep, T* __restrict__ out,
                                                         int out_pitch, float* __restrict__ out_nchw, int cropH,
                                                         int cropW, int vecA, int vecB, int vecO) {
+  PDL_ENTRY();
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Bs[BK][BN];
   const int tid = threadIdx.x;
@@ -204,7 +205,7 @@ void launch_conv_simt(const ConvGeom& g, const T* in, int in_pitch, const float*
   int vecA = (g.Cin % 4 == 0) && (in_pitch % 4 == 0) && (((uintptr_t)in) % vw == 0);
   int vecB = (g.Cout % 4 == 0) && (((uintptr_t)w) % 16 == 0);
   int vecO = out && (out_pitch % 4 == 0) && (((uintptr_t)out) % vw == 0);
-  conv_simt_kernel<T><<<grid, 256, 0, st>>>(g, in, in_pitch, w, ep, out, out_pitch, out_nchw, cropH, cropW, vecA, vecB,
+  pdl_launch(conv_simt_kernel<T>, grid, 256, 0, st, g, in, in_pitch, w, ep, out, out_pitch, out_nchw, cropH, cropW, vecA, vecB,
                                             vecO);
 }
 template void launch_conv_simt<float>(const ConvGeom&, const float*, int, const float*, const Epilogue&, float*, int,

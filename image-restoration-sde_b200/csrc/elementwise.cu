@@ -15,6 +15,7 @@ template <typename T>
 __global__ void prep_input_kernel(const float* __restrict__ xt, const float* __restrict__ cond, T* __restrict__ out,
                                   int B, int C, int H, int W, int Hp, int Wp, int pitch, int conditional,
                                   int pad_top, int pad_left, int row_pix, int img_rows, int zero_pad) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * Hp * Wp;
   if (idx >= total) return;
@@ -46,7 +47,7 @@ void launch_prep_input(const float* xt, const float* cond, T* out, int B, int C,
                        int img_rows, int zero_pad) {
   long long total = (long long)B * Hp * Wp;
   if (row_pix == 0) { row_pix = Wp; img_rows = Hp; }
-  prep_input_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(xt, cond, out, B, C, H, W, Hp, Wp, out_pitch,
+  pdl_launch(prep_input_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, xt, cond, out, B, C, H, W, Hp, Wp, out_pitch,
                                                                          conditional, pad_top, pad_left, row_pix, img_rows, zero_pad);
 }
 template void launch_prep_input<float>(const float*, const float*, float*, int, int, int, int, int, int, int, int,
@@ -57,6 +58,7 @@ template void launch_prep_input<bf16>(const float*, const float*, bf16*, int, in
 template <typename T>
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int B, int C, int H, int W,
                                     int pitch) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * W;
   if (idx >= total) return;
@@ -68,7 +70,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict_
 template <typename T>
 void launch_nchw_to_nhwc(const float* in, T* out, int B, int C, int H, int W, int out_pitch, cudaStream_t st) {
   long long total = (long long)B * H * W;
-  nchw_to_nhwc_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, B, C, H, W, out_pitch);
+  pdl_launch(nchw_to_nhwc_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, in, out, B, C, H, W, out_pitch);
 }
 template void launch_nchw_to_nhwc<float>(const float*, float*, int, int, int, int, int, cudaStream_t);
 template void launch_nchw_to_nhwc<bf16>(const float*, bf16*, int, int, int, int, int, cudaStream_t);
@@ -76,6 +78,7 @@ template void launch_nchw_to_nhwc<bf16>(const float*, bf16*, int, int, int, int,
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int pitch, float* __restrict__ out, int B, int C, int H,
                                     int W) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * H * W;
   if (idx >= total) return;
@@ -86,7 +89,7 @@ __global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, int pitch, float* 
 template <typename T>
 void launch_nhwc_to_nchw(const T* in, int in_pitch, float* out, int B, int C, int H, int W, cudaStream_t st) {
   long long total = (long long)B * H * W;
-  nhwc_to_nchw_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, in_pitch, out, B, C, H, W);
+  pdl_launch(nhwc_to_nchw_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, in, in_pitch, out, B, C, H, W);
 }
 template void launch_nhwc_to_nchw<float>(const float*, int, float*, int, int, int, int, cudaStream_t);
 template void launch_nhwc_to_nchw<bf16>(const bf16*, int, float*, int, int, int, int, cudaStream_t);
@@ -267,6 +270,7 @@ __global__ void sde_update_kernel(int mode, const float* __restrict__ x, const f
                                   const float* __restrict__ coef, const StepState* __restrict__ stp, int t_host,
                                   float* __restrict__ out, long long n, uint64_t seed, long long img_elems,
                                   uint64_t uid_base) {
+  PDL_ENTRY();
   const unsigned long long* uids = nullptr;
   int t = stp ? stp->t : t_host;
   int si = stp ? stp->i : 0;
@@ -296,12 +300,13 @@ void launch_sde_update(int mode, const float* x, const float* mu, const float* n
                        const float* coef, const StepState* st_dev, int t_host, float* out, long long n, uint64_t seed,
                        long long img_elems, uint64_t uid_base, cudaStream_t st) {
   long long groups = (n + 3) / 4;
-  sde_update_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(mode, x, mu, noise, z, z_stride, coef, st_dev,
+  pdl_launch(sde_update_kernel, (unsigned)((groups + 255) / 256), 256, 0, st, mode, x, mu, noise, z, z_stride, coef, st_dev,
                                                                       t_host, out, n, seed, img_elems > 0 ? img_elems : n,
                                                                       uid_base);
 }
 
 __global__ void advance_step_kernel(StepState* s) {
+  PDL_ENTRY();
   s->t -= 1;
   s->i += 1;
 }
@@ -314,7 +319,7 @@ __global__ void set_step_kernel(StepState* s, int t, int i, const float* z, unsi
   s->uid_base = uid_base;
   s->uids = uids;
 }
-void launch_advance_step(StepState* st_dev, cudaStream_t st) { advance_step_kernel<<<1, 1, 0, st>>>(st_dev); }
+void launch_advance_step(StepState* st_dev, cudaStream_t st) { pdl_launch(advance_step_kernel, 1, 1, 0, st, st_dev); }
 void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned long long seed, unsigned long long uid_base,
                      const unsigned long long* uids, cudaStream_t st) {
   set_step_kernel<<<1, 1, 0, st>>>(st_dev, t, i, z, seed, uid_base, uids);
@@ -345,6 +350,7 @@ void launch_noise_state(const float* mu, float* out, long long n, float max_sigm
 // =============================================================================================
 template <typename T>
 __global__ void s2d_kernel(const T* __restrict__ in, int pitch, T* __restrict__ out, int B, int H, int W, int C) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // over B*H*W*(C/8) 16-byte groups
   int vec = 16 / sizeof(T);
   int cg = C / vec;
@@ -363,7 +369,7 @@ template <typename T>
 void launch_space_to_depth(const T* in, int in_pitch, T* out, int B, int H, int W, int C, cudaStream_t st) {
   int vec = 16 / sizeof(T);
   long long total = (long long)B * H * W * (C / vec);
-  s2d_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, in_pitch, out, B, H, W, C);
+  pdl_launch(s2d_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, in, in_pitch, out, B, H, W, C);
 }
 template void launch_space_to_depth<bf16>(const bf16*, int, bf16*, int, int, int, int, cudaStream_t);
 template void launch_space_to_depth<float>(const float*, int, float*, int, int, int, int, cudaStream_t);

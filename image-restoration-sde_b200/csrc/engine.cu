@@ -23,6 +23,10 @@
 
 using namespace irsde;
 
+namespace irsde {
+bool g_pdl = false;  // IRSDE_PDL=1 enables programmatic dependent launch (read in tc_init)
+}
+
 namespace {
 thread_local std::string g_last_error;
 

@@ -19,6 +19,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) dwgate_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ w,
                                                      const float* __restrict__ bias, T* __restrict__ gate, int g_pitch,
                                                      float* __restrict__ partial, int H, int W, int c, int nchunks) {
+  PDL_ENTRY();
   __shared__ float red[4][64];
   const int cl = threadIdx.x & 63, pl = threadIdx.x >> 6;
   const int ch = blockIdx.x * 64 + cl;
@@ -67,6 +68,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) sca_kernel(const float* __restrict__ partial, const float* __restrict__ w,
                                                   const float* __restrict__ bias, float* __restrict__ sca, int c, int nchunks,
                                                   int N, T* __restrict__ g, int g_pitch) {
+  PDL_ENTRY();
   extern __shared__ float mean_s[];
   __shared__ float row_s[8];
   const int b = blockIdx.y;
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(256) sca_kernel(const float* __restrict__ part
 // x[b,p,ch] *= sca[b][ch]   (in place; the "x * self.sca(x)" of :67)
 template <typename T>
 __global__ void scale_channels_kernel(T* __restrict__ x, int pitch, const float* __restrict__ sca, long long npix, int N, int c) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = npix * c;
   if (idx >= total) return;
@@ -111,6 +114,7 @@ __global__ void scale_channels_kernel(T* __restrict__ x, int pitch, const float*
 // SimpleGate on a [.., 2c] tensor -> [.., c]                                   (:9-12)
 template <typename T>
 __global__ void simple_gate_kernel(const T* __restrict__ x, int x_pitch, T* __restrict__ out, int o_pitch, long long npix, int c) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = npix * c;
   if (idx >= total) return;
@@ -124,6 +128,7 @@ __global__ void simple_gate_kernel(const T* __restrict__ x, int x_pitch, T* __re
 template <typename T>
 __global__ void pixel_shuffle_add_kernel(const T* __restrict__ in, int in_pitch, const T* __restrict__ skip, int s_pitch,
                                          T* __restrict__ out, int o_pitch, int B, int h, int w, int q) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = (long long)B * h * w * q;
   if (idx >= total) return;
@@ -145,6 +150,7 @@ __global__ void pixel_shuffle_add_kernel(const T* __restrict__ in, int in_pitch,
 template <typename T>
 __global__ void add_kernel(const T* __restrict__ a, int a_pitch, const T* __restrict__ b, int b_pitch, T* __restrict__ out,
                            int o_pitch, long long npix, int c) {
+  PDL_ENTRY();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   long long total = npix * c;
   if (idx >= total) return;
@@ -160,7 +166,7 @@ template <typename T>
 void launch_dwgate(const T* x, int x_pitch, const float* w, const float* bias, T* gate, int g_pitch, float* partial, int B,
                    int H, int W, int c, cudaStream_t st) {
   const int nchunks = dwgate_chunks(H, W);
-  dwgate_kernel<T><<<dim3((c + 63) / 64, nchunks, B), 256, 0, st>>>(x, x_pitch, w, bias, gate, g_pitch, partial, H, W, c, nchunks);
+  pdl_launch(dwgate_kernel<T>, dim3((c + 63) / 64, nchunks, B), 256, 0, st, x, x_pitch, w, bias, gate, g_pitch, partial, H, W, c, nchunks);
 }
 template void launch_dwgate<float>(const float*, int, const float*, const float*, float*, int, float*, int, int, int, int, cudaStream_t);
 template void launch_dwgate<bf16>(const bf16*, int, const float*, const float*, bf16*, int, float*, int, int, int, int, cudaStream_t);
@@ -174,7 +180,7 @@ template <typename T>
 void launch_sca_scale(const float* partial, const float* w, const float* bias, float* sca, T* g, int g_pitch, int B, int c,
                       int nchunks, int N, int* launches, cudaStream_t st) {
   const bool fused = N <= 1024;
-  sca_kernel<T><<<dim3((c + 7) / 8, B), 256, c * sizeof(float), st>>>(partial, w, bias, sca, c, nchunks, N, fused ? g : (T*)nullptr, g_pitch);
+  pdl_launch(sca_kernel<T>, dim3((c + 7) / 8, B), 256, c * sizeof(float), st, partial, w, bias, sca, c, nchunks, N, fused ? g : (T*)nullptr, g_pitch);
   *launches = 1;
   if (!fused) { launch_scale_channels<T>(g, g_pitch, sca, B, N, c, st); *launches = 2; }
 }
@@ -184,7 +190,7 @@ template void launch_sca_scale<bf16>(const float*, const float*, const float*, f
 template <typename T>
 void launch_scale_channels(T* x, int pitch, const float* sca, int B, int N, int c, cudaStream_t st) {
   long long total = (long long)B * N * c;
-  scale_channels_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, pitch, sca, (long long)B * N, N, c);
+  pdl_launch(scale_channels_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, x, pitch, sca, (long long)B * N, N, c);
 }
 template void launch_scale_channels<float>(float*, int, const float*, int, int, int, cudaStream_t);
 template void launch_scale_channels<bf16>(bf16*, int, const float*, int, int, int, cudaStream_t);
@@ -192,7 +198,7 @@ template void launch_scale_channels<bf16>(bf16*, int, const float*, int, int, in
 template <typename T>
 void launch_simple_gate(const T* x, int x_pitch, T* out, int o_pitch, long long npix, int c, cudaStream_t st) {
   long long total = npix * c;
-  simple_gate_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x, x_pitch, out, o_pitch, npix, c);
+  pdl_launch(simple_gate_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, x, x_pitch, out, o_pitch, npix, c);
 }
 template void launch_simple_gate<float>(const float*, int, float*, int, long long, int, cudaStream_t);
 template void launch_simple_gate<bf16>(const bf16*, int, bf16*, int, long long, int, cudaStream_t);
@@ -201,7 +207,7 @@ template <typename T>
 void launch_pixel_shuffle_add(const T* in, int in_pitch, const T* skip, int s_pitch, T* out, int o_pitch, int B, int h, int w, int q,
                               cudaStream_t st) {
   long long total = (long long)B * h * w * q;
-  pixel_shuffle_add_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, in_pitch, skip, s_pitch, out, o_pitch, B, h, w, q);
+  pdl_launch(pixel_shuffle_add_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, in, in_pitch, skip, s_pitch, out, o_pitch, B, h, w, q);
 }
 template void launch_pixel_shuffle_add<float>(const float*, int, const float*, int, float*, int, int, int, int, int, cudaStream_t);
 template void launch_pixel_shuffle_add<bf16>(const bf16*, int, const bf16*, int, bf16*, int, int, int, int, int, cudaStream_t);
@@ -209,7 +215,7 @@ template void launch_pixel_shuffle_add<bf16>(const bf16*, int, const bf16*, int,
 template <typename T>
 void launch_add(const T* a, int a_pitch, const T* b, int b_pitch, T* out, int o_pitch, long long npix, int c, cudaStream_t st) {
   long long total = npix * c;
-  add_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, a_pitch, b, b_pitch, out, o_pitch, npix, c);
+  pdl_launch(add_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, a, a_pitch, b, b_pitch, out, o_pitch, npix, c);
 }
 template void launch_add<float>(const float*, int, const float*, int, float*, int, long long, int, cudaStream_t);
 template void launch_add<bf16>(const bf16*, int, const bf16*, int, bf16*, int, long long, int, cudaStream_t);
