@@ -11,14 +11,17 @@ namespace irsde {
 // depthwise 3x3 (pad 1, bias) over 2c channels fused with SimpleGate and the SCA pooling partials
 //   gate[b,p,ch] = dw(x)[ch] * dw(x)[ch + c]                   (DenoisingNAFNet_arch.py:65-66)
 //   partial[b][chunk][ch] = sum over the chunk's pixels of gate (AdaptiveAvgPool2d numerator, :29-30)
-// block = 64 channels x 4 pixel lanes, chunk = 64 pixels of one image (deterministic reduction order)
+// block = 64 channels x 4 pixel lanes, chunk = 64 pixels of one image - 16 for images of <= 1024 pixels, where 64-pixel
+// chunks leave a handful of blocks each walking 16 pixels x 9 taps serially (30 us for 512 KB of data at c=512,
+// 16x16) - (deterministic reduction order, fixed by the image shape)
 // =============================================================================================
-static const int DW_PIX = 64;
+static inline int dw_pix(int N) { return N <= 1024 ? 16 : 64; }
 
 template <typename T>
 __global__ void __launch_bounds__(256) dwgate_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ w,
                                                      const float* __restrict__ bias, T* __restrict__ gate, int g_pitch,
-                                                     float* __restrict__ partial, int H, int W, int c, int nchunks) {
+                                                     float* __restrict__ partial, int H, int W, int c, int nchunks,
+                                                     int DW_PIX) {
   PDL_ENTRY();
   __shared__ float red[4][64];
   const int cl = threadIdx.x & 63, pl = threadIdx.x >> 6;
@@ -160,13 +163,14 @@ __global__ void add_kernel(const T* __restrict__ a, int a_pitch, const T* __rest
 }
 
 // ---- launchers -------------------------------------------------------------------------------------
-int dwgate_chunks(int H, int W) { return (H * W + DW_PIX - 1) / DW_PIX; }
+int dwgate_chunks(int H, int W) { return (H * W + dw_pix(H * W) - 1) / dw_pix(H * W); }
 
 template <typename T>
 void launch_dwgate(const T* x, int x_pitch, const float* w, const float* bias, T* gate, int g_pitch, float* partial, int B,
                    int H, int W, int c, cudaStream_t st) {
   const int nchunks = dwgate_chunks(H, W);
-  pdl_launch(dwgate_kernel<T>, dim3((c + 63) / 64, nchunks, B), 256, 0, st, x, x_pitch, w, bias, gate, g_pitch, partial, H, W, c, nchunks);
+  pdl_launch(dwgate_kernel<T>, dim3((c + 63) / 64, nchunks, B), 256, 0, st, x, x_pitch, w, bias, gate, g_pitch, partial, H, W, c, nchunks,
+             dw_pix(H * W));
 }
 template void launch_dwgate<float>(const float*, int, const float*, const float*, float*, int, float*, int, int, int, int, cudaStream_t);
 template void launch_dwgate<bf16>(const bf16*, int, const float*, const float*, bf16*, int, float*, int, int, int, int, cudaStream_t);
