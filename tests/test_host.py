@@ -99,6 +99,14 @@ def _worker(rank, world, port, q):
     zs = torch.arange(4 * 5 * 3 * 2 * 2, dtype=torch.float32).reshape(4, 5, 3, 2, 2)
     run = lambda x, m, z: x * 2 + m + z.sum(0)  # stand-in for the per-rank chain (needs no GPU)
     out = irsde_b200.sharded_reverse(run, xT, mu, zs)
+
+    class FakeSde:  # in-kernel Philox path: the rank's first global image index must be the image base during the run
+        image_base = 100
+    seen = []
+    run2 = lambda x, m, z: (seen.append((FakeSde.image_base, x.shape[0], z is None)), x + 1)[1]
+    out2 = irsde_b200.sharded_reverse(run2, xT, mu, None, sde=FakeSde)
+    lo, hi = irsde_b200.shard_range(5, rank, world)
+    assert seen == [(100 + lo, hi - lo, True)] and FakeSde.image_base == 100 and torch.equal(out2, xT + 1)
     lin = torch.nn.Linear(4, 4)
     if rank != 0:
         with torch.no_grad():
