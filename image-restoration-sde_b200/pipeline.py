@@ -90,11 +90,11 @@ class Restorer:
 
     def restore(self, images, first_uid=0):
         """List of uint8 [H,W,3] (BGR, the cv2 order) numpy images -> list of restored uint8 images, same order."""
-        if not torch.cuda.is_available():
-            raise RuntimeError("irsde_b200.Restorer runs on CUDA (sm_100a) only; there is no CPU path")
         for im in images:
             if not (isinstance(im, np.ndarray) and im.dtype == np.uint8 and im.ndim == 3):
                 raise TypeError("images must be uint8 numpy arrays [H,W,C]")
+        if not torch.cuda.is_available():
+            raise RuntimeError("irsde_b200.Restorer runs on CUDA (sm_100a) only; there is no CPU path")
         batches = plan_batches([im.shape for im in images], self.batch_size)
         out = [None] * len(images)
         with torch.cuda.device(self.device):

@@ -203,3 +203,46 @@ def test_sde_diagnostic_helpers_match_reference_algebra():
     assert torch.equal(ds.sde_reverse_drift(x, sc, t), -0.5 * ds.sigmas[t] ** 2 * (1 + Ad) * sc * ds.dt)
     assert torch.equal(ds.ode_reverse_drift(x, sc, t), -0.5 * ds.sigmas[t] ** 2 * Ad * sc * ds.dt)
     assert torch.equal(ds.drift(x, mu, t), ds.thetas[t] * (mu - x) * ds.dt)
+
+
+def test_state_dict_contract_nafnet_and_latent():
+    """ConditionalNAFNet (both variants) and the latent UNet register exactly the reference's state-dict keys/shapes
+    (fixtures hold the reference modules' own state_dict), so `load_state_dict(strict=True)` of reference checkpoints works."""
+    import irsde_b200
+    gd = os.path.join(os.path.dirname(__file__), "golden")
+    naf = torch.load(os.path.join(gd, "reference_golden_nafnet.pt"), weights_only=False)
+    for key, g in naf.items():
+        if not (isinstance(g, dict) and "state" in g):
+            continue
+        net = irsde_b200.ConditionalNAFNet(latent=g["latent"], **g["cfg"])
+        assert list(net.state_dict().keys()) == list(g["state"].keys()), key
+        assert all(tuple(net.state_dict()[k].shape) == tuple(v.shape) for k, v in g["state"].items())
+        net.load_state_dict(g["state"], strict=True)
+    lat = torch.load(os.path.join(gd, "reference_golden_latent.pt"), weights_only=False)
+    ae = irsde_b200.UNet(**lat["cfg"])
+    assert list(ae.state_dict().keys()) == list(lat["state"].keys())
+    ae.load_state_dict(lat["state"], strict=True)
+    from oracle import irsde_oracle as O
+    c = lat["cfg"]
+    assert irsde_b200.latent_unet_param_shapes(c["in_ch"], c["out_ch"], c["ch"], c["ch_mult"], c["embed_dim"]) == \
+        {k: tuple(v) for k, v in O.latent_unet_param_shapes(c["in_ch"], c["out_ch"], c["ch"], c["ch_mult"], c["embed_dim"]).items()}
+
+
+def test_front_end_needs_cuda():
+    """imaging / Restorer / latent UNet have no CPU path: they raise instead of silently computing on the host."""
+    import numpy as np
+    import irsde_b200
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    img = np.zeros((16, 16, 3), np.uint8)
+    with pytest.raises(RuntimeError):
+        irsde_b200.tensor2img(torch.zeros(3, 16, 16))
+    with pytest.raises(RuntimeError):
+        irsde_b200.calculate_psnr(img, img)
+    with pytest.raises(RuntimeError):
+        irsde_b200.UNet(3, 3, 8, [1, 2], 4).encode(torch.zeros(1, 3, 16, 16))
+    sde = irsde_b200.IRSDE(10, 4, device="cpu")
+    with pytest.raises(RuntimeError):
+        irsde_b200.Restorer(sde, device="cpu").restore([img])
+    with pytest.raises(TypeError):
+        irsde_b200.Restorer(sde, device="cpu").restore([img.astype(np.float32)])
