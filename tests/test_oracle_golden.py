@@ -150,6 +150,21 @@ def test_latent_unet_oracle_real_checkpoint():
     # the well-conditioned random-weight fixture (test_latent_unet_oracle_vs_reference).
     assert y.shape == x.shape
     assert list(O.latent_unet_param_shapes(3, 3, 8, [4, 8, 8, 16], 8)) == list(sd)
+    # A natural image (images/1.png crop): the oracle follows the reference's fp32 op order closely enough to reproduce
+    # its decode to 1e-5 of the output range, although that range is ~78 and the reference's fp32 and fp64 runs differ by
+    # 0.17 in z and ~67 in y here - the checkpoint is ill-conditioned, so this pins the restatement, not a tolerance a
+    # re-ordered fp32 implementation (the GPU kernels) can be held to.
+    import cv2
+    import numpy as np
+    img = cv2.imread("/root/reference/images/1.png")
+    xi = torch.from_numpy(img[:, :, [2, 1, 0]].astype(np.float32) / 255.).permute(2, 0, 1)[None][:, :, :160, :224].contiguous()
+    with torch.no_grad():
+        zi, hi = net.encode(xi)
+        yi = net.decode(zi, hi)
+    zo, ho = O.latent_unet_encode(sd, xi, [4, 8, 8, 16])
+    yo = O.latent_unet_decode(sd, zo, ho, [4, 8, 8, 16], 160, 224)
+    _close(zo, zi, 1e-4)
+    assert (yo - yi).abs().max().item() < 1e-4 * yi.abs().max().item()
 
 
 # ---- image helpers (oracle/imaging_oracle.py vs the reference's img_utils outputs) ---------------------------
