@@ -80,17 +80,46 @@ class ClockSampler:
                 "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def build_info():
+    d = {}
+    try:
+        for line in open(os.path.join(ROOT, "image-restoration-sde_b200", "BUILD_INFO")):
+            k, _, v = line.strip().partition("=")
+            d[k] = v
+    except Exception:
+        pass
+    return d
+
+
 def ncu_traffic_per_launch():
-    """Mean DRAM bytes (read + write) per tcgen05 conv launch from the committed `ncu --set full` capture of this
-    workload (profiles/), or None when the summary is absent.  Not measured live: ncu cannot run inside a timed bench."""
+    """(mean DRAM bytes (read + write) per tcgen05 conv launch, source description) from the newest committed
+    `ncu --set full` capture of this workload (profiles/rNN_conv_tc_ncu_full_one_step.csv + .meta.json), or (None, why).
+    Not measured live: ncu cannot run inside a timed bench.  The description carries the commit / source hash the capture
+    was taken from and whether that equals the build being timed."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_final_conv_tc_ncu_full_one_step.csv")
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_conv_tc_ncu_full_one_step.csv")))
+    files = [f for f in files if "_v1_" not in f]
+    if not files:
+        return None, "no profiles/r*_conv_tc_ncu_full_one_step.csv"
+    path = files[-1]
     try:
         rows = list(csv.DictReader(open(path)))[1:]   # first row holds the units (Mbyte)
         tot = sum(float(r["dram__bytes_read.sum"]) + float(r["dram__bytes_write.sum"]) for r in rows)
-        return tot * 1e6 / len(rows)
-    except Exception:
-        return None
+        meta = {}
+        try:
+            meta = json.load(open(path[:-4] + ".meta.json"))
+        except Exception:
+            pass
+        bi = build_info()
+        same = bool(meta.get("csrc_sha256")) and meta.get("csrc_sha256") == bi.get("csrc_sha256")
+        src = ("%s: mean dram read+write bytes per launch over %d launches of one step, ncu --set full; captured from commit %s "
+               "(csrc %s); this build: commit %s (csrc %s) -> %s" % (
+                   os.path.relpath(path, ROOT), len(rows), meta.get("commit", "?"), meta.get("csrc_sha256", "?"),
+                   bi.get("commit", "?"), bi.get("csrc_sha256", "?"), "same sources" if same else "DIFFERENT sources"))
+        return tot * 1e6 / len(rows), src
+    except Exception as e:
+        return None, "unreadable %s: %s" % (path, e)
 
 
 def usable_cores():
@@ -279,6 +308,7 @@ def run_b200(args):
                                 "tflops": (fl_a[i] / (ms_a[i] * 1e-3) / 1e12) if ms_a[i] > 0 and fl_a[i] > 0 else None}
                      for i in range(ncat) if n_a[i] > 0}
         k = 0 if n_a[0] > 0 else 1
+        traffic, traffic_src = ncu_traffic_per_launch()
         if ms_a[k] > 0:
             ach = fl_a[k] / (ms_a[k] * 1e-3) / 1e12
             pk = peak_tf if k == 0 else 75.0
@@ -286,9 +316,8 @@ def run_b200(args):
                     "bound": "tensor", "achieved": ach, "peak": pk, "unit": "TFLOP/s", "frac": ach / pk,
                     "peak_source": peak_src if k == 0 else "nominal fp32 FMA peak",
                     "flops_per_launch": fl_a[k] / n_a[k], "avg_launch_ms": ms_a[k] / n_a[k], "launches": int(n_a[k]),
-                    "share_of_step": ms_a[k] / sum(ms_a), "traffic": ncu_traffic_per_launch() if k == 0 else None,
-                    "traffic_source": "profiles/r01_final_conv_tc_ncu_full_one_step.csv: mean dram read+write bytes per "
-                                      "launch over one step's launches, ncu --set full capture of this workload",
+                    "share_of_step": ms_a[k] / sum(ms_a), "traffic": traffic if k == 0 else None,
+                    "traffic_source": traffic_src,
                     "how": "CUDA events around each launch, %d sampler steps, non-graph pass after the timed region" % prof_steps}
 
     # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same workload on host cores

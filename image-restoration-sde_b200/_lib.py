@@ -18,8 +18,9 @@ NUM_COEF = 8
 SYMBOLS = ["irsde_create", "irsde_create_nafnet", "irsde_create_latent_unet", "irsde_latent_shape", "irsde_latent_encode",
            "irsde_latent_decode", "irsde_tensor2img_u8", "irsde_img2tensor_u8", "irsde_sqerr_u8", "irsde_ssim_workspace", "irsde_ssim_u8", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
            "irsde_finalize_weights", "irsde_set_schedule", "irsde_set_coeffs", "irsde_noise_fn", "irsde_step",
-           "irsde_reverse", "irsde_noise_state", "irsde_noise_state_images", "irsde_set_image_base", "irsde_set_image_uids", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
-           "irsde_profile_end"]
+           "irsde_reverse", "irsde_noise_state", "irsde_noise_state_images", "irsde_set_image_base", "irsde_set_image_uids", "irsde_comm_unique_id", "irsde_comm_init", "irsde_broadcast_weights", "irsde_gather", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
+           "irsde_profile_end", "irsde_conv2d_ex", "irsde_plan_num_ops", "irsde_plan_op_info", "irsde_trace_forward",
+           "irsde_trim"]
 
 
 class Config(ctypes.Structure):
@@ -77,6 +78,24 @@ def load():
     L.irsde_device_bytes.restype = i64
     L.irsde_conv2d.argtypes = [vp, i32, vp, vp, vp, vp] + [i32] * 11 + [vp]
     L.irsde_conv2d.restype = ctypes.c_int
+    L.irsde_conv2d_ex.argtypes = [vp, i32, vp, vp, vp, vp, vp] + [i32] * 12 + [vp]
+    L.irsde_conv2d_ex.restype = ctypes.c_int
+    L.irsde_plan_num_ops.argtypes = [vp, i32, i32, i32]
+    L.irsde_plan_num_ops.restype = i32
+    L.irsde_plan_op_info.argtypes = [vp, i32, i32, i32, i32, ctypes.c_char_p, i32, ctypes.POINTER(i32)]
+    L.irsde_plan_op_info.restype = ctypes.c_int
+    L.irsde_trace_forward.argtypes = [vp, vp, vp, fp, i32, i32, i32, i32, i32, vp, vp]
+    L.irsde_trace_forward.restype = ctypes.c_int
+    L.irsde_comm_unique_id.argtypes = [vp]
+    L.irsde_comm_unique_id.restype = ctypes.c_int
+    L.irsde_comm_init.argtypes = [vp, vp, i32, i32]
+    L.irsde_comm_init.restype = ctypes.c_int
+    L.irsde_broadcast_weights.argtypes = [vp, i32, vp]
+    L.irsde_broadcast_weights.restype = ctypes.c_int
+    L.irsde_gather.argtypes = [vp, vp, vp, ctypes.POINTER(i64), vp]
+    L.irsde_gather.restype = ctypes.c_int
+    L.irsde_trim.argtypes = [vp]
+    L.irsde_trim.restype = ctypes.c_int
     L.irsde_profile_begin.argtypes = [vp]
     L.irsde_profile_begin.restype = ctypes.c_int
     L.irsde_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),

@@ -20,8 +20,32 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def csrc_sha256():
+    """Hash of the CUDA sources + the C header: names the build a profile was captured from (profiles/*.meta.json)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(CSRC)):
+        if f.endswith((".cu", ".cuh")):
+            h.update(f.encode())
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+    h.update(open(os.path.join(HERE, "..", "include", "irsde_b200.h"), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def _write_build_info():
+    try:
+        commit = subprocess.run(["git", "-C", HERE, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
+        dirty = bool(subprocess.run(["git", "-C", HERE, "status", "--porcelain", "--", "csrc", "../include"], capture_output=True,
+                                    text=True).stdout.strip())
+    except Exception:
+        commit, dirty = "", False
+    with open(os.path.join(HERE, "BUILD_INFO"), "w") as f:
+        f.write("commit=%s%s\ncsrc_sha256=%s\n" % (commit or "unknown", "+dirty" if dirty else "", csrc_sha256()))
+
+
 def build(force=False, verbose=False):
     if not force and not _stale():
+        _write_build_info()
         return LIB
     objs = []
     procs = []
@@ -40,6 +64,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc failed building libirsde_b200.so")
     cmd = [NVCC, "-shared", "-cudart", "static", "-o", LIB] + objs + ["-ldl", "-lpthread", "-lrt"]
     subprocess.check_call(cmd)
+    _write_build_info()
     return LIB
 
 

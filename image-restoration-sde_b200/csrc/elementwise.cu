@@ -280,11 +280,28 @@ __global__ void sde_update_kernel(int mode, const float* __restrict__ x, const f
   bool need_z = (mode == 0 || mode == 2 || mode == 3);
   if (stp) { z = stp->z; seed = stp->seed; uid_base = stp->uid_base; uids = stp->uids; }
   const float* zz = z ? z + (long long)si * z_stride : nullptr;
+  const bool vec4 = (((uintptr_t)x | (uintptr_t)noise | (uintptr_t)out | (uintptr_t)mu | (uintptr_t)zz) & 15) == 0;
   long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // group of 4 elements
   long long i0 = q * 4;
   if (i0 >= n) return;
   float zr[4] = {0.f, 0.f, 0.f, 0.f};
   if (need_z && !zz) image_normals(seed, uid_base, uids, i0, img_elems, (uint32_t)t, zr);
+  if (vec4 && i0 + 3 < n) {  // 128-bit loads/stores: every operand is 16-byte aligned and the group is complete
+    const float4 xv = *reinterpret_cast<const float4*>(x + i0);
+    const float4 ev = *reinterpret_cast<const float4*>(noise + i0);
+    const float4 mv = mu ? *reinterpret_cast<const float4*>(mu + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (need_z && zz) {
+      const float4 zv = *reinterpret_cast<const float4*>(zz + i0);
+      zr[0] = zv.x; zr[1] = zv.y; zr[2] = zv.z; zr[3] = zv.w;
+    }
+    float4 o;
+    o.x = sde_update_one(mode, c, xv.x, mv.x, ev.x, zr[0]);
+    o.y = sde_update_one(mode, c, xv.y, mv.y, ev.y, zr[1]);
+    o.z = sde_update_one(mode, c, xv.z, mv.z, ev.z, zr[2]);
+    o.w = sde_update_one(mode, c, xv.w, mv.w, ev.w, zr[3]);
+    *reinterpret_cast<float4*>(out + i0) = o;
+    return;
+  }
 #pragma unroll
   for (int k = 0; k < 4; ++k) {
     long long i = i0 + k;

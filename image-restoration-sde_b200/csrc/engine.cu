@@ -5,6 +5,7 @@
 // UNet (DenoisingUNet_arch.py:118,121,127) are channel-offset views into one pre-allocated buffer
 // (producers write at their channel offset: no torch.cat copies) and so that a 64-channel slab of a
 // pixel row is one 128-byte line (the TMA / UMMA swizzle atom of the tensor-core engine).
+#include <dlfcn.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -54,6 +55,9 @@ struct OpRec {
   Op fn;
   std::string label;   // for IRSDE_PROFILE_DUMP
   double bytes = 0.0;  // algorithmic HBM bytes (inputs + outputs + weights once)
+  // NHWC view this op writes (irsde_trace_forward reads it back right after the op ran); null for fp32-NCHW outputs
+  const void* out_p = nullptr;
+  int out_pitch = 0, out_C = 0, out_H = 0, out_W = 0;
 };
 
 struct Plan {
@@ -73,6 +77,8 @@ struct Plan {
   int chain_cap = 0;
   cudaGraphExec_t graph[IRSDE_NUM_MODES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   long long step_launches[IRSDE_NUM_MODES] = {0, 0, 0, 0, 0};
+  long long bytes = 0;               // device memory owned by this plan (plan cache accounting)
+  unsigned long long last_use = 0;   // LRU stamp
 };
 }  // namespace
 
@@ -108,9 +114,13 @@ struct irsde_ctx {
   float dt = 0, max_sigma = 0;
   std::vector<float> thetas, sigmas, cumsum, sbars;
   float* coef_dev[IRSDE_NUM_MODES] = {nullptr, nullptr, nullptr, nullptr, nullptr};
-  std::map<std::tuple<int, int, int>, Plan*> plans;
+  std::map<std::tuple<int, int, int>, Plan*> plans;  // LRU-bounded cache, see build_plan()
+  unsigned long long use_clock = 0;
+  long long plan_bytes = 0;
   long long launches = 0;
   unsigned long long image_base = 0;  // uid of the first image of the next batch (Philox key; irsde_set_image_base)
+  void* nccl_comm = nullptr;             // ncclComm_t (irsde_comm_init)
+  int comm_rank = 0, comm_nranks = 1;
   unsigned long long* d_uids = nullptr;  // explicit per-image uids (irsde_set_image_uids), capacity MAX_UIDS
   int n_uids = 0;                        // 0: uid = image_base + b
   long long dev_bytes = 0;
@@ -474,6 +484,10 @@ struct Builder {
 
   struct V { T* p; int pitch; int C; };  // channel-offset NHWC view
   static V view(T* base, int pitch, int off, int C) { return V{base + off, pitch, C}; }
+  void mark_out(V out, int H, int W) {  // the op just pushed writes this view (irsde_trace_forward)
+    OpRec& r = plan->ops.back();
+    r.out_p = out.p; r.out_pitch = out.pitch; r.out_C = out.C; r.out_H = H; r.out_W = W;
+  }
 
   // generic conv op. ss_block = ResBlock prefix whose (scale,shift) modulate the output ("" = none)
   void conv(const std::string& wname, V in, int Hin, int Win, int K, int stride, int pad, int up, const char* bias,
@@ -487,6 +501,7 @@ struct Builder {
       int Ho = (Hin * up + 2 * pad - K) / stride + 1, Wo = (Win * up + 2 * pad - K) / stride + 1;
       snprintf(b, sizeof b, "%s %dx%d k%d s%d up%d Cin%d Cout%d", wname.c_str(), Hin, Win, K, stride, up, in.C, Cout);
       r.label = b;
+      if (!out_nchw_slot) { r.out_p = out.p; r.out_pitch = out.pitch; r.out_C = Cout; r.out_H = Ho; r.out_W = Wo; }
       double esz = sizeof(T);
       r.bytes = (double)plan->B * Hin * Win * in.C * esz + (double)plan->B * Ho * Wo * Cout * (out_nchw_slot ? 4.0 : esz) +
                 (double)K * K * in.C * Cout * esz + (res ? (double)plan->B * Ho * Wo * Cout * esz : 0.0);
@@ -625,6 +640,7 @@ struct Builder {
     }});
     plan->ops.back().label = pre + "norm";
     plan->ops.back().bytes = 2.0 * npix * C * sizeof(T);
+    mark_out(V{xn, C, C}, H, W);
     T* qkv = tmp(npix * 384);
     if constexpr (std::is_same<T, bf16>::value) {
       if (!full && ctx->use_tc && tc_fused_attention_available() && C % 8 == 0) {
@@ -658,6 +674,7 @@ struct Builder {
         }});
         plan->ops.back().label = pre + "to_out.norm+res";
         plan->ops.back().bytes = 3.0 * npix * C * sizeof(T);
+        mark_out(out, H, W);
         release(y);
         release(Mb);
         release(qkv);
@@ -672,6 +689,8 @@ struct Builder {
         launch_fullattn<T>(qkv, 384, hid, 128, B, N, st);
         c->launches++;
       }});
+      plan->ops.back().label = pre + "full attention";
+      mark_out(V{hid, 128, 128}, H, W);
       std::string bn = pre + "fn.fn.to_out.bias";
       conv(pre + "fn.fn.to_out.weight", V{hid, 128, 128}, H, W, 1, 1, 0, 1, bn.c_str(), "", 0, &in, out, C);
     } else {
@@ -691,6 +710,7 @@ struct Builder {
       }});
       plan->ops.back().label = pre + "to_out.norm+res";
       plan->ops.back().bytes = 3.0 * npix * C * sizeof(T);
+      mark_out(out, H, W);
       release(y);
     }
     release(qkv);
@@ -1081,11 +1101,46 @@ struct Builder {
   }
 };
 
+void free_plan(irsde_ctx* ctx, Plan* p) {
+  for (int m = 0; m < IRSDE_NUM_MODES; ++m)
+    if (p->graph[m]) cudaGraphExecDestroy(p->graph[m]);
+  for (auto* d : p->tc_descs) tc_conv_destroy(d);
+  for (void* q : p->allocs) cudaFree(q);  // cudaFree waits for in-flight work that may still use the buffer
+  ctx->dev_bytes -= p->bytes;
+  ctx->plan_bytes -= p->bytes;
+  delete p;
+}
+
+// The plan cache is bounded: every (B,H,W) plan owns its activation workspace, TMA descriptors and step graphs, so a
+// loop over a dataset of variable-size images (test.py runs batch 1 at native size) would otherwise grow without limit.
+// Least-recently-used plans are dropped while the cache holds more than IRSDE_PLAN_CACHE_MB (default 24576) or
+// IRSDE_PLAN_CACHE_MAX (default 8) entries; `keep` is never evicted.
+void evict_plans(irsde_ctx* ctx, Plan* keep, bool all) {
+  static long long budget = -1, maxn = -1;
+  if (budget < 0) {
+    const char* e = getenv("IRSDE_PLAN_CACHE_MB");
+    budget = (e && atoll(e) > 0 ? atoll(e) : 24576LL) << 20;
+    e = getenv("IRSDE_PLAN_CACHE_MAX");
+    maxn = e && atoll(e) > 0 ? atoll(e) : 8;
+  }
+  for (;;) {
+    const bool over = all || ctx->plan_bytes > budget || (long long)ctx->plans.size() > maxn;
+    if (!over) return;
+    auto victim = ctx->plans.end();
+    for (auto it = ctx->plans.begin(); it != ctx->plans.end(); ++it)
+      if (it->second != keep && (victim == ctx->plans.end() || it->second->last_use < victim->second->last_use)) victim = it;
+    if (victim == ctx->plans.end()) return;
+    free_plan(ctx, victim->second);
+    ctx->plans.erase(victim);
+  }
+}
+
 int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
   auto key = std::make_tuple(B, H, W);
   auto it = ctx->plans.find(key);
-  if (it != ctx->plans.end()) { *out = it->second; return IRSDE_OK; }
+  if (it != ctx->plans.end()) { it->second->last_use = ++ctx->use_clock; *out = it->second; return IRSDE_OK; }
   if (B <= 0 || H <= 0 || W <= 0) return fail(ctx, IRSDE_ERR_INVALID, "bad image shape");
+  const long long bytes_before = ctx->dev_bytes;
   int s = 1 << ctx->cfg.depth;
   // reflect pad needs pad < size (F.pad 'reflect' raises otherwise, DenoisingUNet_arch.py:82)
   if (!ctx->naf.on && ((s - H % s) % s >= H || (s - W % s) % s >= W))
@@ -1115,12 +1170,18 @@ int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
   p->fwd_temb = (float*)dev_alloc(ctx, (size_t)B * td * 4, &p->allocs);
   p->fwd_table = (float*)dev_alloc(ctx, (size_t)B * ctx->S * 4, &p->allocs);
   if (!ok || !p->x_state || !p->mu_buf || !p->eps_buf || !p->d_step || !p->d_zero || !p->fwd_table) {
+    for (auto* d : p->tc_descs) tc_conv_destroy(d);
     for (void* q : p->allocs) cudaFree(q);
+    ctx->dev_bytes = bytes_before;
     delete p;
     return fail(ctx, IRSDE_ERR_CUDA, err.empty() ? "plan allocation failed" : err);
   }
   cudaMemset(p->d_zero, 0, sizeof(int));
+  p->bytes = ctx->dev_bytes - bytes_before;
+  p->last_use = ++ctx->use_clock;
+  ctx->plan_bytes += p->bytes;
   ctx->plans[key] = p;
+  evict_plans(ctx, p, false);
   *out = p;
   return IRSDE_OK;
 }
@@ -1190,6 +1251,7 @@ int upload_coeffs(irsde_ctx* ctx, int mode, const float* tab, int T) {
     if (!ctx->coef_dev[mode]) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc coef failed");
   }
   if (T > 4096) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "T > 4096 not supported");
+  CUDA_TRY(ctx, cudaDeviceSynchronize());  // chains in flight on non-blocking streams still read the old table
   CUDA_TRY(ctx, cudaMemcpy(ctx->coef_dev[mode], tab, bytes, cudaMemcpyHostToDevice));
   return IRSDE_OK;
 }
@@ -1217,6 +1279,7 @@ int ensure_chain_table(irsde_ctx* ctx, Plan* p, int T, cudaStream_t st) {
     p->chain_temb = (float*)dev_alloc(ctx, (size_t)cap * td * 4, &p->allocs);
     p->chain_table = (float*)dev_alloc(ctx, (size_t)cap * ctx->S * 4, &p->allocs);
     if (!p->chain_times || !p->chain_temb || !p->chain_table) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc chain table failed");
+    { const long long add = ((long long)cap * 4 + (long long)cap * td * 4 + (long long)cap * ctx->S * 4); p->bytes += add; ctx->plan_bytes += add; }
     std::vector<float> tv(cap);
     for (int i = 0; i < cap; ++i) tv[i] = (float)i;
     CUDA_TRY(ctx, cudaMemcpy(p->chain_times, tv.data(), (size_t)cap * 4, cudaMemcpyHostToDevice));
@@ -1349,18 +1412,121 @@ int irsde_create_nafnet(const irsde_nafnet_config* ncfg, irsde_ctx** out) {
   return IRSDE_OK;
 }
 
+// ---- NCCL behind the C ABI (SURVEY 8 b): dlopen()ed on first use so that single-GPU users keep a library without
+// an NCCL dependency.  Only the two collectives of the path: one weight broadcast, one gather of x0. ----------------
+struct NcclId { char internal[128]; };  // ncclUniqueId (NCCL_UNIQUE_ID_BYTES = 128), passed by value like the original
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, NcclId, int) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+}  // namespace
+namespace {
+NcclApi g_nccl;
+const int kNcclFloat = 7;  // ncclFloat32
+bool nccl_load(std::string* err) {
+  if (g_nccl.lib) return true;
+  const char* names[] = {getenv("IRSDE_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+  void* h = nullptr;
+  for (const char* n : names)
+    if (n && n[0] && (h = dlopen(n, RTLD_NOW | RTLD_GLOBAL))) break;
+  if (!h) { *err = "libnccl.so.2 not found (set IRSDE_NCCL_LIB)"; return false; }
+  NcclApi a;
+  a.lib = h;
+  a.GetUniqueId = (int (*)(void*))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (int (*)(void**, int, NcclId, int))dlsym(h, "ncclCommInitRank");
+  a.CommDestroy = (int (*)(void*))dlsym(h, "ncclCommDestroy");
+  a.Broadcast = (int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t))dlsym(h, "ncclBroadcast");
+  a.GroupStart = (int (*)())dlsym(h, "ncclGroupStart");
+  a.GroupEnd = (int (*)())dlsym(h, "ncclGroupEnd");
+  a.GetErrorString = (const char* (*)(int))dlsym(h, "ncclGetErrorString");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.CommDestroy || !a.Broadcast || !a.GroupStart || !a.GroupEnd) { *err = "incomplete NCCL library"; return false; }
+  g_nccl = a;
+  return true;
+}
+int nccl_fail(irsde_ctx* ctx, const char* what, int rc) {
+  return fail(ctx, IRSDE_ERR_CUDA, std::string(what) + ": " + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "NCCL error"));
+}
+}  // namespace
+
+int irsde_comm_unique_id(void* id128) {
+  std::string err;
+  if (!id128) return fail(nullptr, IRSDE_ERR_INVALID, "null id buffer");
+  if (!nccl_load(&err)) return fail(nullptr, IRSDE_ERR_UNSUPPORTED, err);
+  int rc = g_nccl.GetUniqueId(id128);
+  return rc ? nccl_fail(nullptr, "ncclGetUniqueId", rc) : IRSDE_OK;
+}
+
+int irsde_comm_init(irsde_ctx* ctx, const void* id128, int32_t rank, int32_t nranks) {
+  if (!ctx || !id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  if (ctx->nccl_comm) return fail(ctx, IRSDE_ERR_STATE, "communicator already initialised");
+  std::string err;
+  if (!nccl_load(&err)) return fail(ctx, IRSDE_ERR_UNSUPPORTED, err);
+  cudaSetDevice(ctx->cfg.device);
+  NcclId id;
+  memcpy(id.internal, id128, sizeof id.internal);
+  int rc = g_nccl.CommInitRank(&ctx->nccl_comm, nranks, id, rank);
+  if (rc) { ctx->nccl_comm = nullptr; return nccl_fail(ctx, "ncclCommInitRank", rc); }
+  ctx->comm_rank = rank; ctx->comm_nranks = nranks;
+  return IRSDE_OK;
+}
+
+int irsde_broadcast_weights(irsde_ctx* ctx, int32_t src, void* stream) {
+  if (!ctx || !ctx->nccl_comm) return fail(ctx, IRSDE_ERR_STATE, "irsde_comm_init first");
+  if (src < 0 || src >= ctx->comm_nranks) return fail(ctx, IRSDE_ERR_INVALID, "bad source rank");
+  if (ctx->raw.empty()) return fail(ctx, IRSDE_ERR_STATE, "load a state dict of the architecture on every rank first");
+  cudaSetDevice(ctx->cfg.device);
+  // every rank has loaded a state dict of the same names/shapes (std::map: same iteration order on every rank); the raw
+  // fp32 tensors are overwritten in place inside ONE NCCL group (a single fused launch), then repacked for the kernels
+  CUDA_TRY(ctx, cudaDeviceSynchronize());  // chains in flight still read the packed weights
+  int rc = g_nccl.GroupStart();
+  if (rc) return nccl_fail(ctx, "ncclGroupStart", rc);
+  for (auto& kv : ctx->raw) {
+    rc = g_nccl.Broadcast(kv.second.dev, kv.second.dev, (size_t)kv.second.numel, kNcclFloat, src, ctx->nccl_comm, (cudaStream_t)stream);
+    if (rc) { g_nccl.GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
+  }
+  rc = g_nccl.GroupEnd();
+  if (rc) return nccl_fail(ctx, "ncclGroupEnd", rc);
+  CUDA_TRY(ctx, cudaStreamSynchronize((cudaStream_t)stream));
+  ctx->finalized = false;
+  return irsde_finalize_weights(ctx);
+}
+
+int irsde_gather(irsde_ctx* ctx, const float* x_local, float* x_all, const int64_t* counts, void* stream) {
+  if (!ctx || !ctx->nccl_comm) return fail(ctx, IRSDE_ERR_STATE, "irsde_comm_init first");
+  if (!x_all || !counts) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  cudaSetDevice(ctx->cfg.device);
+  // rank r's slice (counts[r] floats; the contiguous batch partition may be ragged) lands at the running offset in
+  // x_all on EVERY rank: one broadcast per root inside a single group = an all-gather with per-rank counts
+  int rc = g_nccl.GroupStart();
+  if (rc) return nccl_fail(ctx, "ncclGroupStart", rc);
+  int64_t off = 0;
+  for (int r = 0; r < ctx->comm_nranks; ++r) {
+    if (counts[r] < 0 || (r == ctx->comm_rank && counts[r] > 0 && !x_local)) { g_nccl.GroupEnd(); return fail(ctx, IRSDE_ERR_INVALID, "bad counts"); }
+    if (counts[r] > 0) {
+      rc = g_nccl.Broadcast(r == ctx->comm_rank ? (const void*)x_local : (const void*)(x_all + off), x_all + off, (size_t)counts[r],
+                            kNcclFloat, r, ctx->nccl_comm, (cudaStream_t)stream);
+      if (rc) { g_nccl.GroupEnd(); return nccl_fail(ctx, "ncclBroadcast", rc); }
+    }
+    off += counts[r];
+  }
+  rc = g_nccl.GroupEnd();
+  return rc ? nccl_fail(ctx, "ncclGroupEnd", rc) : IRSDE_OK;
+}
+
 void irsde_destroy(irsde_ctx* ctx) {
   if (!ctx) return;
+  if (ctx->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->nccl_comm);
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
-  for (auto& kv : ctx->plans) {
-    Plan* p = kv.second;
-    for (int m = 0; m < IRSDE_NUM_MODES; ++m)
-      if (p->graph[m]) cudaGraphExecDestroy(p->graph[m]);
-    for (auto* d : p->tc_descs) tc_conv_destroy(d);
-    for (void* q : p->allocs) cudaFree(q);
-    delete p;
-  }
+  for (auto& kv : ctx->plans) free_plan(ctx, kv.second);
+  ctx->plans.clear();
   for (void* q : ctx->allocs) cudaFree(q);
   delete ctx;
 }
@@ -1368,6 +1534,10 @@ void irsde_destroy(irsde_ctx* ctx) {
 int irsde_load_tensor(irsde_ctx* ctx, const char* name, const void* data, int32_t ndim, const int64_t* shape) {
   if (!ctx || !name || !data || ndim < 0 || ndim > 4) return fail(ctx, IRSDE_ERR_INVALID, "bad argument to irsde_load_tensor");
   cudaSetDevice(ctx->cfg.device);
+  // Weights are pointer-stable buffers that captured step graphs read: a re-upload (load_state_dict, broadcast) must not
+  // overtake chains still in flight on the caller's (possibly non-blocking) streams.  The first tensor of an upload
+  // round drains the device; the copies below are synchronous, so later launches see the new values.
+  if (ctx->finalized || ctx->raw.empty()) CUDA_TRY(ctx, cudaDeviceSynchronize());
   long long n = 1;
   std::vector<int64_t> sh(shape, shape + ndim);
   for (auto d : sh) n *= d;
@@ -1665,13 +1835,83 @@ int irsde_profile_end(irsde_ctx* ctx, double* ms, double* flops, int64_t* launch
   return IRSDE_OK;
 }
 
+int irsde_trim(irsde_ctx* ctx) {
+  if (!ctx) return fail(nullptr, IRSDE_ERR_INVALID, "null ctx");
+  cudaSetDevice(ctx->cfg.device);
+  evict_plans(ctx, nullptr, true);
+  return IRSDE_OK;
+}
+
+int32_t irsde_plan_num_ops(irsde_ctx* ctx, int32_t B, int32_t H, int32_t W) {
+  if (!ctx) return fail(nullptr, IRSDE_ERR_INVALID, "null ctx");
+  if (!ctx->finalized) return fail(ctx, IRSDE_ERR_STATE, "weights not finalized");
+  cudaSetDevice(ctx->cfg.device);
+  Plan* p;
+  int rc = build_plan(ctx, B, H, W, &p);
+  return rc ? rc : (int32_t)p->ops.size();
+}
+
+int irsde_plan_op_info(irsde_ctx* ctx, int32_t B, int32_t H, int32_t W, int32_t op, char* label, int32_t label_cap,
+                       int32_t* dims) {
+  if (!ctx || !label || label_cap < 1 || !dims) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
+  if (!ctx->finalized) return fail(ctx, IRSDE_ERR_STATE, "weights not finalized");
+  cudaSetDevice(ctx->cfg.device);
+  Plan* p;
+  int rc = build_plan(ctx, B, H, W, &p);
+  if (rc) return rc;
+  if (op < 0 || op >= (int)p->ops.size()) return fail(ctx, IRSDE_ERR_INVALID, "op index out of range");
+  const OpRec& r = p->ops[op];
+  snprintf(label, (size_t)label_cap, "%s", r.label.c_str());
+  dims[0] = r.out_p ? r.out_C : 0; dims[1] = r.out_H; dims[2] = r.out_W; dims[3] = r.cat;
+  return IRSDE_OK;
+}
+
+int irsde_trace_forward(irsde_ctx* ctx, const float* x, const float* mu, const float* times, int32_t n_times, int32_t B,
+                        int32_t H, int32_t W, int32_t op, float* dump, void* stream) {
+  if (!ctx || !x || !times || !dump) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
+  if (!ctx->finalized) return fail(ctx, IRSDE_ERR_STATE, "weights not finalized");
+  if (ctx->cfg.variant == IRSDE_NET_CONDITIONAL && !ctx->lat.on && !mu) return fail(ctx, IRSDE_ERR_INVALID, "mu required");
+  if (n_times != 1 && n_times != B) return fail(ctx, IRSDE_ERR_INVALID, "n_times must be 1 or B");
+  cudaSetDevice(ctx->cfg.device);
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan* p;
+  int rc = build_plan(ctx, B, H, W, &p);
+  if (rc) return rc;
+  if (op < 0 || op >= (int)p->ops.size()) return fail(ctx, IRSDE_ERR_INVALID, "op index out of range");
+  const OpRec& r = p->ops[op];
+  if (!r.out_p) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "this op has no NHWC output view to read back");
+  CUDA_TRY(ctx, cudaMemcpyAsync(p->fwd_times, times, (size_t)n_times * 4, cudaMemcpyHostToDevice, st));
+  time_rows(ctx, p->fwd_times, n_times, p->fwd_temb, p->fwd_table, st);
+  p->cur.x = x; p->cur.mu = mu; p->cur.out = p->eps_buf;
+  p->cur.ss = p->fwd_table; p->cur.t_ptr = p->d_zero; p->cur.ss_img_stride = (n_times > 1) ? 1 : 0;
+  for (int i = 0; i <= op; ++i) p->ops[i].fn(p, st);
+  if (ctx->cfg.precision == IRSDE_PREC_FP32)
+    launch_nhwc_to_nchw<float>((const float*)r.out_p, r.out_pitch, dump, B, r.out_C, r.out_H, r.out_W, st);
+  else
+    launch_nhwc_to_nchw<bf16>((const bf16*)r.out_p, r.out_pitch, dump, B, r.out_C, r.out_H, r.out_W, st);
+  CUDA_TRY(ctx, cudaGetLastError());
+  return IRSDE_OK;
+}
+
 int64_t irsde_launch_count(const irsde_ctx* ctx) { return ctx ? ctx->launches : 0; }
 int64_t irsde_device_bytes(const irsde_ctx* ctx) { return ctx ? ctx->dev_bytes : 0; }
 
 int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w, const float* bias, float* y, int32_t B,
                  int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride, int32_t pad,
                  int32_t upsample, int32_t silu, void* stream) {
+  return irsde_conv2d_ex(ctx, engine, x, w, bias, nullptr, y, B, Cin, H, W, Cout, KH, KW, stride, pad, upsample, silu, 0, stream);
+}
+
+int irsde_conv2d_ex(irsde_ctx* ctx, int32_t engine, const float* x, const float* w, const float* bias, const float* residual,
+                    float* y, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                    int32_t pad, int32_t upsample, int32_t silu, int32_t flags, void* stream) {
   if (!ctx || !x || !w || !y) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
+  const bool f_qsm = (flags & IRSDE_CONV_QSOFTMAX) != 0, f_wimg = (flags & IRSDE_CONV_W_PER_IMAGE) != 0;
+  if ((f_qsm || f_wimg || residual) && engine != 1)
+    return fail(ctx, IRSDE_ERR_UNSUPPORTED, "flags / residual are epilogues of the tensor-core engine");
+  if ((f_qsm || f_wimg) && !(KH == 1 && KW == 1 && stride == 1 && pad == 0 && !upsample && Cout % 8 == 0))
+    return fail(ctx, IRSDE_ERR_INVALID, "q-softmax / per-image weights need a 1x1 conv with Cout % 8 == 0");
+  if (f_qsm && Cout < 128) return fail(ctx, IRSDE_ERR_INVALID, "q-softmax needs Cout >= 128 (4 heads x 32)");
   cudaSetDevice(ctx->cfg.device);
   cudaStream_t st = (cudaStream_t)stream;
   int up = upsample ? 2 : 1;
@@ -1691,6 +1931,15 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
     long long nin = k7 ? (long long)B * (H + 6) * (W + 8) * 8 + 64 : (long long)B * H * W * Cin;
     long long nw = (long long)Cout * Cin * KH * KW, nout = (long long)B * Ho * Wo * Cout_pad;
     long long nwt = (k3 && up == 2) ? (long long)16 * Cout * Cin : (k7 ? (long long)7 * Cout * 64 : (long long)Cout_pad * Cin * KH * KW);
+    if (f_wimg) nwt *= B;  // w is [B][Cout][Cin]
+    (void)nw;
+    bf16* resb = nullptr;
+    if (residual) {
+      if (nchw) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "residual needs Cout % 8 == 0");
+      resb = (bf16*)dev_alloc(ctx, nout * 2, &tmp);
+      if (!resb) { for (void* q : tmp) cudaFree(q); return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed"); }
+      launch_nchw_to_nhwc<bf16>(residual, resb, B, Cout, Ho, Wo, Cout, st);
+    }
     bf16* xin = (bf16*)dev_alloc(ctx, nin * 2, &tmp);
     bf16* xs2d = (bf16*)dev_alloc(ctx, nin * 2, &tmp);
     bf16* wp = (bf16*)dev_alloc(ctx, nwt * 2, &tmp);
@@ -1706,6 +1955,7 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
       } else {
         launch_nchw_to_nhwc<bf16>(x, xin, B, Cin, H, W, Cin, st);
         if (k3 && up == 2) pack_tc_up_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cin);
+        else if (f_wimg) pack_tc_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, B * Cout, Cin, 1, 1);
         else pack_tc_padded_kernel<<<(unsigned)((nwt + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cout_pad, Cin, KH, KW);
       }
       TcTap taps[16];
@@ -1726,7 +1976,9 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
       memset(&ep, 0, sizeof ep);
       ep.bias = bias;
       ep.silu = silu;
-      d = tc_conv_create(a_ptr, a_pitch, B, Ha, Wa, Ca, planes, wp, Cout, ntaps, taps, nph, ep, nchw ? nullptr : yo, Cout, Ho, Wo, &terr);
+      if (resb) { ep.res = resb; ep.res_pitch = Cout; }
+      d = tc_conv_create(a_ptr, a_pitch, B, Ha, Wa, Ca, planes, wp, Cout, ntaps, taps, nph, ep, nchw ? nullptr : yo, Cout, Ho, Wo, &terr,
+                         (f_qsm ? TC_FLAG_QSOFTMAX : 0) | (f_wimg ? TC_FLAG_W_PER_IMAGE : 0));
       if (!d) rc = fail(ctx, IRSDE_ERR_INVALID, "tc_conv_create: " + terr);
     }
     if (!rc) {

@@ -6,8 +6,12 @@ communication, and x0 is gathered once at the end.  This replaces the reference'
 ``DataParallel`` (models/denoising_model.py:41-42), which re-broadcasts all parameters and
 scatters/gathers the batch on every one of the T forwards.
 """
+import ctypes
+
 import torch
 import torch.distributed as dist
+
+from . import _lib
 
 
 def shard_range(B, rank, world):
@@ -63,3 +67,41 @@ def sharded_reverse(run, xT, mu=None, zs=None, group=None, gather=True, sde=None
     bufs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(bufs, pad, group=group)
     return torch.cat([bufs[r][:sizes[r][1] - sizes[r][0]] for r in range(world)], dim=0)
+
+
+# ---- NCCL behind the C ABI (include/irsde_b200.h: irsde_comm_*) -------------------------------------------------------
+def comm_unique_id():
+    """128-byte NCCL id (bytes); rank 0 creates it and hands it to the other ranks out of band (file, pipe, TCP store)."""
+    buf = ctypes.create_string_buffer(128)
+    _lib.check(_lib.load().irsde_comm_unique_id(buf))
+    return bytes(buf.raw)
+
+
+class NativeComm:
+    """The path's two collectives through the library's own NCCL communicator, for hosts that do not use
+    torch.distributed: ``broadcast_weights`` once, T steps with no communication, one ``gather`` of x0."""
+
+    def __init__(self, model, uid, rank, nranks, device=None):
+        self.model, self.rank, self.nranks = model, rank, nranks
+        self.ctx = model.sync_weights(device)
+        _lib.check(self.ctx.L.irsde_comm_init(self.ctx.h, uid, rank, nranks), self.ctx.h)
+
+    def broadcast_weights(self, src=0):
+        """Rank ``src``'s parameters replace every rank's inside the native context (one NCCL group); the nn.Module's
+        own tensors are refreshed from it lazily only if the caller asks (``pull=True`` is not needed for sampling)."""
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.ctx.L.irsde_broadcast_weights(self.ctx.h, src, ctypes.c_void_p(st)), self.ctx.h)
+
+    def gather(self, x_local, B_total):
+        """All ranks receive the [B_total, ...] batch in rank order (the contiguous partition of ``shard_range``)."""
+        per = x_local[0].numel() if x_local.shape[0] else 0
+        sizes = [shard_range(B_total, r, self.nranks) for r in range(self.nranks)]
+        if per == 0:
+            raise ValueError("gather needs at least one image per rank to learn the image shape")
+        counts = (ctypes.c_int64 * self.nranks)(*[(hi - lo) * per for lo, hi in sizes])
+        x_local = x_local.contiguous().float()
+        out = torch.empty((B_total,) + tuple(x_local.shape[1:]), device=x_local.device, dtype=torch.float32)
+        st = torch.cuda.current_stream().cuda_stream
+        _lib.check(self.ctx.L.irsde_gather(self.ctx.h, ctypes.c_void_p(x_local.data_ptr()), ctypes.c_void_p(out.data_ptr()), counts,
+                                           ctypes.c_void_p(st)), self.ctx.h)
+        return out

@@ -94,8 +94,8 @@ class _LatContext(_lib.Context):
 class LatentSkips:
     """Opaque stand-in for the reference's skip list ``h``: (owner module, input shape)."""
 
-    def __init__(self, owner, shape, gen):
-        self.owner, self.shape, self.gen = owner, tuple(shape), gen
+    def __init__(self, owner, shape, gen, ctx=None):
+        self.owner, self.shape, self.gen, self.ctx = owner, tuple(shape), gen, ctx
 
 
 class UNet(ConditionalUNet):
@@ -154,7 +154,7 @@ class UNet(ConditionalUNet):
                                                  ctypes.c_void_p(st)), ctx.h)
         self.H, self.W = H, W
         self._gen = getattr(self, "_gen", 0) + 1
-        return z, LatentSkips(self, (B, H, W), self._gen)
+        return z, LatentSkips(self, (B, H, W), self._gen, ctx)
 
     @torch.no_grad()
     def decode(self, x, h):
@@ -164,8 +164,18 @@ class UNet(ConditionalUNet):
             raise RuntimeError("stale skip handle: a later encode() overwrote the device-resident skips "
                                "(one outstanding encode per module)")
         B, H, W = h.shape
+        if not x.is_cuda:
+            raise RuntimeError("irsde_b200.UNet runs on CUDA (sm_100a) only; there is no CPU path")
         x = x.contiguous().float()
         ctx = self.sync_weights(x.device)
+        if ctx is not h.ctx:
+            raise RuntimeError("stale skip handle: the module moved to another device since encode()")
+        lh, lw = ctypes.c_int32(), ctypes.c_int32()
+        _lib.check(ctx.L.irsde_latent_shape(ctx.h, H, W, ctypes.byref(lh), ctypes.byref(lw)), ctx.h)
+        if tuple(x.shape) != (B, self.embed_dim, lh.value, lw.value):
+            # the library reads B*embed*lat_h*lat_w floats from x: a wrong-shaped latent would be an out-of-bounds read
+            raise ValueError("latent must be %s for the %s input these skips came from, got %s"
+                             % ((B, self.embed_dim, lh.value, lw.value), (B, self.in_ch, H, W), tuple(x.shape)))
         out = torch.empty((B, self.out_ch, H, W), device=x.device, dtype=torch.float32)
         with torch.cuda.device(x.device):
             st = torch.cuda.current_stream().cuda_stream

@@ -55,7 +55,9 @@ class _SDEBase:
         self.mu = 0.
         self.model = None
         self._step_ctx = None
-        self._sched_on = None  # id of the context the schedule was last uploaded to
+        _SDEBase._next_uid = getattr(_SDEBase, "_next_uid", 0) + 1
+        self._uid = _SDEBase._next_uid  # never reused, unlike id(): names this sampler as the owner of uploaded tables
+        self._coeff_cache = {}
         self.use_graph = os.environ.get("IRSDE_B200_GRAPH", "1") != "0"
         self.rng = os.environ.get("IRSDE_B200_RNG", "torch")  # "torch": randn_like per step; "philox": in-kernel
         self.seed = 0
@@ -99,16 +101,23 @@ class _SDEBase:
         return tab
 
     def _upload_schedule(self, ctx):
-        if self._sched_on == id(ctx):
+        # The tables live in the native context, which belongs to the MODEL: two samplers sharing one network
+        # (IRSDE(T=100) and IRSDE(T=50), different max_sigma / eps ...) would otherwise run on each other's
+        # thetas / sigma_bars / coefficients.  Ownership is recorded on the context object itself (not by id(): ids
+        # are reused after a context is closed) and the tables are re-uploaded whenever another sampler wrote last.
+        sig = (self._uid, self.T, float(self.max_sigma), float(self.dt))
+        if getattr(ctx, "_sched_sig", None) == sig:
             return
         c = self._cpu
         fa = lambda t: _lib.float_array(t.tolist())
         _lib.check(ctx.L.irsde_set_schedule(ctx.h, fa(c["thetas"]), fa(c["sigmas"]), fa(c["thetas_cumsum"]),
                                             fa(c["sigma_bars"]), float(self.dt), float(self.max_sigma), self.T), ctx.h)
         for mode in self._modes:
-            tab = self._coeff_table(mode).reshape(-1)
+            if mode not in self._coeff_cache:
+                self._coeff_cache[mode] = self._coeff_table(mode).reshape(-1).tolist()
+            tab = torch.tensor(self._coeff_cache[mode])
             _lib.check(ctx.L.irsde_set_coeffs(ctx.h, mode, _lib.float_array(tab.tolist()), self.T), ctx.h)
-        self._sched_on = id(ctx)
+        ctx._sched_sig = sig
 
     def _ctx_for(self, x):
         """Native context used for the update kernel: the model's if it is ours, else a private one."""
@@ -142,8 +151,8 @@ class _SDEBase:
         noise = noise.contiguous().float()
         out = torch.empty_like(x)
         p = lambda a: ctypes.c_void_p(a.data_ptr()) if a is not None else None
-        if mu is not None:
-            mu = mu.to(x.device).expand_as(x).contiguous().float()
+        if mu is not None:  # IRSDE starts with mu = 0. (a Python float, like the reference): broadcast it
+            mu = torch.as_tensor(mu, dtype=torch.float32, device=x.device).expand_as(x).contiguous()
         if z is not None:
             z = z.contiguous().float()
         with torch.cuda.device(x.device):
@@ -159,7 +168,7 @@ class _SDEBase:
         x = xt.contiguous().float()
         B, C, H, W = x.shape
         if mu is not None:
-            mu = mu.to(x.device).expand_as(x).contiguous().float()
+            mu = torch.as_tensor(mu, dtype=torch.float32, device=x.device).expand_as(x).contiguous()
         need_z = mode in (_lib.MODE_SDE, _lib.MODE_POSTERIOR, _lib.MODE_DSDE_SDE)
         if need_z and zs is None and self.rng == "torch":
             # same generator calls as the reference: one randn_like(x) per step in loop order

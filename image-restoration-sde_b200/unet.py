@@ -194,6 +194,39 @@ class ConditionalUNet(nn.Module):
     def forward(self, xt, cond, time):
         return self._run(xt, cond, time)
 
+    # ---- parity instrumentation (C ABI: irsde_plan_num_ops / irsde_plan_op_info / irsde_trace_forward) ------------
+    def plan_ops(self, B, H, W, device=None):
+        """[(label, (C, H, W) of the NHWC view the op writes or None, category)] of the launch plan for a [B,*,H,W] input."""
+        import ctypes
+        ctx = self.sync_weights(device)
+        n = ctx.L.irsde_plan_num_ops(ctx.h, B, H, W)
+        if n < 0:
+            _lib.check(n, ctx.h)
+        ops, buf, dims = [], ctypes.create_string_buffer(256), (ctypes.c_int32 * 4)()
+        for i in range(n):
+            _lib.check(ctx.L.irsde_plan_op_info(ctx.h, B, H, W, i, buf, 256, dims), ctx.h)
+            ops.append((buf.value.decode(), (dims[0], dims[1], dims[2]) if dims[0] else None, dims[3]))
+        return ops
+
+    @torch.no_grad()
+    def trace(self, xt, cond, time, op):
+        """Output of op `op` of the forward (fp32 [B,C,H,W]); runs ops 0..op."""
+        import ctypes
+        x = xt.contiguous().float()
+        cond = cond.to(x.device).contiguous().float() if cond is not None else None
+        B, _, H, W = x.shape
+        ctx = self.sync_weights(x.device)
+        buf, dims = ctypes.create_string_buffer(256), (ctypes.c_int32 * 4)()
+        _lib.check(ctx.L.irsde_plan_op_info(ctx.h, B, H, W, op, buf, 256, dims), ctx.h)
+        out = torch.empty((B, dims[0], dims[1], dims[2]), device=x.device, dtype=torch.float32)
+        arr = _lib.float_array(self._times(time, B))
+        with torch.cuda.device(x.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(ctx.L.irsde_trace_forward(ctx.h, ctypes.c_void_p(x.data_ptr()),
+                                                 ctypes.c_void_p(cond.data_ptr()) if cond is not None else None, arr, len(arr),
+                                                 B, H, W, op, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(st)), ctx.h)
+        return out
+
     def launch_count(self):
         return int(self._ctx.L.irsde_launch_count(self._ctx.h)) if self._ctx else 0
 

@@ -180,6 +180,49 @@ int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w,
                  int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
                  int32_t pad, int32_t upsample, int32_t silu, void* stream);
 
+/* Same with the tensor-core engine's fused epilogues (engine must be 1 when any is used):
+ *   residual  fp32 [B,Cout,Ho,Wo] added after the activation (ResBlock `h + res_conv(x)`, module_util.py:146), or NULL;
+ *   IRSDE_CONV_QSOFTMAX     1x1 conv whose first 128 output channels are LinearAttention's q: softmax over each
+ *                           32-channel head times 32^-0.5 (module_util.py:168,171);
+ *   IRSDE_CONV_W_PER_IMAGE  w is [B,Cout,Cin]: image b is multiplied by its own matrix (LinearAttention's second einsum
+ *                           + to_out re-associated, module_util.py:176-178). */
+#define IRSDE_CONV_QSOFTMAX 1
+#define IRSDE_CONV_W_PER_IMAGE 2
+int irsde_conv2d_ex(irsde_ctx* ctx, int32_t engine, const float* x, const float* w, const float* bias, const float* residual,
+                    float* y, int32_t B, int32_t Cin, int32_t H, int32_t W, int32_t Cout, int32_t KH, int32_t KW,
+                    int32_t stride, int32_t pad, int32_t upsample, int32_t silu, int32_t flags, void* stream);
+
+/* ---- launch-plan introspection (parity instrumentation: per-layer comparison with the oracle) ----
+ * The network forward for a (B,H,W) input is a fixed list of ops.  irsde_plan_num_ops returns its length (or a negative
+ * irsde_status); irsde_plan_op_info gives op `op`'s label (the state-dict name of the weight it applies, e.g.
+ * "downs.0.0.block1.proj.weight 256x256 k3 ...") and dims = {C, H, W of the NHWC view it writes (C == 0: none),
+ * category as in irsde_profile_end}; irsde_trace_forward runs ops 0..op of `irsde_noise_fn(x, mu, times)` and writes
+ * op `op`'s output as fp32 [B,C,H,W] to `dump` (device). */
+int32_t irsde_plan_num_ops(irsde_ctx* ctx, int32_t B, int32_t H, int32_t W);
+int irsde_plan_op_info(irsde_ctx* ctx, int32_t B, int32_t H, int32_t W, int32_t op, char* label, int32_t label_cap,
+                       int32_t* dims /* [4] */);
+int irsde_trace_forward(irsde_ctx* ctx, const float* x, const float* mu, const float* times, int32_t n_times, int32_t B,
+                        int32_t H, int32_t W, int32_t op, float* dump, void* stream);
+
+/* Drop every cached (B,H,W) launch plan (activation workspaces, TMA descriptors, step graphs).  The cache is also
+ * bounded on its own: least-recently-used plans are evicted beyond IRSDE_PLAN_CACHE_MB (default 24576) megabytes or
+ * IRSDE_PLAN_CACHE_MAX (default 8) entries, so looping over variable-size images (codes/config/<task>/test.py:96-130,
+ * batch 1 at native resolution) does not grow device memory without limit. */
+int irsde_trim(irsde_ctx* ctx);
+
+/* ---- multi-GPU plumbing (one process per GPU; SURVEY.md 8 b, e) ------------------------------------------------
+ * Replaces DataParallel's per-step replicate / scatter / gather (models/denoising_model.py:41-42) with the two
+ * collectives the path needs.  NCCL is dlopen()ed on first use (IRSDE_NCCL_LIB overrides the soname) so single-GPU users
+ * keep a library without an NCCL dependency; ranks exchange the 128-byte id out of band (rank 0 creates it).
+ * irsde_broadcast_weights: every rank has loaded a state dict of the same names/shapes; the fp32 tensors are replaced
+ * by rank `src`'s in one NCCL group and repacked (irsde_finalize_weights is called inside).
+ * irsde_gather: rank r contributes counts[r] floats (its slice of x0 in the contiguous batch partition, which may be
+ * ragged); x_all receives all slices in rank order = batch order, on every rank. */
+int irsde_comm_unique_id(void* id128);
+int irsde_comm_init(irsde_ctx* ctx, const void* id128, int32_t rank, int32_t nranks);
+int irsde_broadcast_weights(irsde_ctx* ctx, int32_t src, void* stream);
+int irsde_gather(irsde_ctx* ctx, const float* x_local, float* x_all, const int64_t* counts /* [nranks] */, void* stream);
+
 /* ---- image conversion and full-reference metrics on the device -------------------
  * Stateless (no ctx): errors are reported through the return code and irsde_last_error(NULL).
  * Replaces util.tensor2img (codes/utils/img_utils.py:136-163), img2tensor / read_img's "/255." (:171-180,

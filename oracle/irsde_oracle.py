@@ -184,22 +184,31 @@ def layer_norm_c(x, g):
     return (x - mean) * (var + 1e-5).rsqrt() * g
 
 
-def res_block(P, pre, x, temb):
+def _tr(trace, key, val):
+    """Per-layer checkpoints for the GPU parity report (tests/): keyed by the state-dict name of the weight whose
+    (fused) output this is, the same key the CUDA launch plan labels its ops with."""
+    if trace is not None:
+        trace[key] = val
+    return val
+
+
+def res_block(P, pre, x, temb, trace=None):
     """ResBlock / Block.  module_util.py:108-146 (convs bias-free, res_conv 1x1 or identity)."""
     ss = F.linear(_silu(temb), P[pre + "mlp.1.weight"], P[pre + "mlp.1.bias"])
     scale, shift = ss[:, :, None, None].chunk(2, dim=1)
     h = F.conv2d(x, P[pre + "block1.proj.weight"], padding=1)
-    h = _silu(h * (scale + 1) + shift)
+    h = _tr(trace, pre + "block1.proj.weight", _silu(h * (scale + 1) + shift))
     h = _silu(F.conv2d(h, P[pre + "block2.proj.weight"], padding=1))
     if (pre + "res_conv.weight") in P:
-        x = F.conv2d(x, P[pre + "res_conv.weight"])
-    return h + x
+        x = _tr(trace, pre + "res_conv.weight", F.conv2d(x, P[pre + "res_conv.weight"]))
+    return _tr(trace, pre + "block2.proj.weight", h + x)
 
 
-def linear_attention(P, pre, x, heads=4, dim_head=32):
+def linear_attention(P, pre, x, heads=4, dim_head=32, trace=None):
     """Residual(PreNorm(LinearAttention)).  module_util.py:20-26,82-90,150-178."""
     b, c, hh, ww = x.shape
-    xn = layer_norm_c(x, P[pre + "norm.g"])
+    base = pre[:-3]  # "downs.0.2.fn." -> "downs.0.2."
+    xn = _tr(trace, base + "norm", layer_norm_c(x, P[pre + "norm.g"]))
     qkv = F.conv2d(xn, P[pre + "fn.to_qkv.weight"])
     q, k, v = [t.reshape(b, heads, dim_head, hh * ww) for t in qkv.chunk(3, dim=1)]
     q = q.softmax(dim=-2) * dim_head ** -0.5
@@ -207,27 +216,28 @@ def linear_attention(P, pre, x, heads=4, dim_head=32):
     v = v / (hh * ww)
     ctx = torch.einsum("bhdn,bhen->bhde", k, v)
     out = torch.einsum("bhde,bhdn->bhen", ctx, q).reshape(b, heads * dim_head, hh, ww)
-    out = F.conv2d(out, P[pre + "fn.to_out.0.weight"], P[pre + "fn.to_out.0.bias"])
+    out = _tr(trace, pre + "fn.to_out.0.weight", F.conv2d(out, P[pre + "fn.to_out.0.weight"], P[pre + "fn.to_out.0.bias"]))
     out = layer_norm_c(out, P[pre + "fn.to_out.1.g"])
-    return out + x
+    return _tr(trace, base + "to_out.norm+res", out + x)
 
 
-def full_attention(P, pre, x, heads=4, dim_head=32):
+def full_attention(P, pre, x, heads=4, dim_head=32, trace=None):
     """Residual(PreNorm(Attention)) - denoising-sde mid_attn only.  module_util.py:182-204."""
     b, c, hh, ww = x.shape
-    xn = layer_norm_c(x, P[pre + "norm.g"])
+    base = pre[:-3]
+    xn = _tr(trace, base + "norm", layer_norm_c(x, P[pre + "norm.g"]))
     qkv = F.conv2d(xn, P[pre + "fn.to_qkv.weight"])
     q, k, v = [t.reshape(b, heads, dim_head, hh * ww) for t in qkv.chunk(3, dim=1)]
     q = q * dim_head ** -0.5
     sim = torch.einsum("bhdi,bhdj->bhij", q, k)
     attn = sim.softmax(dim=-1)
     out = torch.einsum("bhij,bhdj->bhid", attn, v)
-    out = out.permute(0, 1, 3, 2).reshape(b, heads * dim_head, hh, ww)
+    out = _tr(trace, base + "full attention", out.permute(0, 1, 3, 2).reshape(b, heads * dim_head, hh, ww))
     out = F.conv2d(out, P[pre + "fn.to_out.weight"], P[pre + "fn.to_out.bias"])
-    return out + x
+    return _tr(trace, pre + "fn.to_out.weight", out + x)
 
 
-def unet_forward(P, xt, cond, time, nf, depth, variant="conditional"):
+def unet_forward(P, xt, cond, time, nf, depth, variant="conditional", trace=None):
     """ConditionalUNet.forward.  codes/config/deraining/models/modules/DenoisingUNet_arch.py:85-134
     (variant="conditional": input cat(xt-cond, cond)); the denoising-sde variant
     (codes/config/denoising-sde/models/modules/DenoisingUNet_arch.py:84-132) takes x only and
@@ -243,42 +253,42 @@ def unet_forward(P, xt, cond, time, nf, depth, variant="conditional"):
     H, W = x.shape[2:]
     s = 2 ** depth
     x = F.pad(x, (0, (s - W % s) % s, 0, (s - H % s) % s), "reflect")
-    x = F.conv2d(x, P["init_conv.weight"], padding=3)
+    x = _tr(trace, "init_conv.weight", F.conv2d(x, P["init_conv.weight"], padding=3))
     x_ = x
     temb = time_embedding(P, time.to(torch.float32) if time.dtype.is_floating_point else time, nf)
     h = []
     for i in range(depth):
         pre = "downs.%d." % i
-        x = res_block(P, pre + "0.", x, temb)
+        x = res_block(P, pre + "0.", x, temb, trace)
         h.append(x)
-        x = res_block(P, pre + "1.", x, temb)
-        x = linear_attention(P, pre + "2.fn.", x)
+        x = res_block(P, pre + "1.", x, temb, trace)
+        x = linear_attention(P, pre + "2.fn.", x, trace=trace)
         h.append(x)
         if i != depth - 1:
-            x = F.conv2d(x, P[pre + "3.weight"], P[pre + "3.bias"], stride=2, padding=1)
+            x = _tr(trace, pre + "3.weight", F.conv2d(x, P[pre + "3.weight"], P[pre + "3.bias"], stride=2, padding=1))
         else:
-            x = F.conv2d(x, P[pre + "3.weight"], padding=1)
-    x = res_block(P, "mid_block1.", x, temb)
+            x = _tr(trace, pre + "3.weight", F.conv2d(x, P[pre + "3.weight"], padding=1))
+    x = res_block(P, "mid_block1.", x, temb, trace)
     if variant == "conditional":
-        x = linear_attention(P, "mid_attn.fn.", x)
+        x = linear_attention(P, "mid_attn.fn.", x, trace=trace)
     else:
-        x = full_attention(P, "mid_attn.fn.", x)
-    x = res_block(P, "mid_block2.", x, temb)
+        x = full_attention(P, "mid_attn.fn.", x, trace=trace)
+    x = res_block(P, "mid_block2.", x, temb, trace)
     for j in range(depth):
         i = depth - 1 - j
         pre = "ups.%d." % j
         x = torch.cat([x, h.pop()], dim=1)
-        x = res_block(P, pre + "0.", x, temb)
+        x = res_block(P, pre + "0.", x, temb, trace)
         x = torch.cat([x, h.pop()], dim=1)
-        x = res_block(P, pre + "1.", x, temb)
-        x = linear_attention(P, pre + "2.fn.", x)
+        x = res_block(P, pre + "1.", x, temb, trace)
+        x = linear_attention(P, pre + "2.fn.", x, trace=trace)
         if i != 0:
             x = F.interpolate(x, scale_factor=2, mode="nearest")
-            x = F.conv2d(x, P[pre + "3.1.weight"], P[pre + "3.1.bias"], padding=1)
+            x = _tr(trace, pre + "3.1.weight", F.conv2d(x, P[pre + "3.1.weight"], P[pre + "3.1.bias"], padding=1))
         else:
-            x = F.conv2d(x, P[pre + "3.weight"], padding=1)
+            x = _tr(trace, pre + "3.weight", F.conv2d(x, P[pre + "3.weight"], padding=1))
     x = torch.cat([x, x_], dim=1)
-    x = res_block(P, "final_res_block.", x, temb)
+    x = res_block(P, "final_res_block.", x, temb, trace)
     x = F.conv2d(x, P["final_conv.weight"], P["final_conv.bias"], padding=1)
     return x[..., :H, :W]
 

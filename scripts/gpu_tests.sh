@@ -2,7 +2,7 @@
 # GPU test driver used under gpurun: separate processes so a trapped kernel cannot poison later groups.
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-timeout 900 python -m pytest tests -q -m gpu -k "not tcgen05 and not bf16" -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/t_fp32.log
-timeout 600 python -m pytest tests -q -m gpu -k "tcgen05" -x -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/t_tc.log
-timeout 600 python -m pytest tests -q -m gpu -k "bf16" -p no:cacheprovider 2>&1 | tail -40 > gpurun_out/t_bf16.log
-tail -5 gpurun_out/t_fp32.log gpurun_out/t_tc.log gpurun_out/t_bf16.log
+nproc >> gpurun_out/smi.txt
+timeout 900 python -m pytest tests/test_gpu_bench_shapes.py -q -m gpu -p no:cacheprovider 2>&1 | tail -150 > gpurun_out/t_bench_shapes.log
+timeout 900 python -m pytest tests -q -m gpu --deselect tests/test_gpu_bench_shapes.py -p no:cacheprovider 2>&1 | tail -60 > gpurun_out/t_rest.log
+tail -5 gpurun_out/t_bench_shapes.log gpurun_out/t_rest.log

@@ -318,7 +318,7 @@ def test_step_bf16_teacher_forced(lib, golden):
 @pytest.fixture(scope="module")
 def golden_naf():
     import os
-    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_nafnet.pt"), weights_only=False)
+    return torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_nafnet.pt"), weights_only=True)
 
 
 @pytest.mark.parametrize("key", ["nafnet", "nafnet_latent"])
@@ -414,7 +414,7 @@ def test_full_size_properties_bf16(lib):
 def test_latent_unet_fp32_vs_reference(lib):
     import os
     dev = _dev()
-    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_latent.pt"), weights_only=False)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_latent.pt"), weights_only=True)
     net = lib.UNet(precision="fp32", **g["cfg"])
     assert list(net.state_dict().keys()) == list(g["state"].keys())
     net.load_state_dict(g["state"], strict=True)
@@ -561,3 +561,63 @@ def test_restorer_batched_equals_single(lib, precision):
     sde.image_uids = None
     assert np.array_equal(lib.Restorer(sde, mode="ode", batch_size=3).restore(imgs)[2],
                           lib.Restorer(sde, mode="ode", batch_size=1).restore(imgs)[2])
+
+
+# ------------------------------------------------------------------------------------------------
+# context hygiene (round-1 advisor findings)
+# ------------------------------------------------------------------------------------------------
+def test_two_samplers_share_one_network(lib, golden):
+    """The schedule / coefficient tables live in the MODEL's native context: two samplers with different T and max_sigma
+    driving one network must each see their own tables, in any interleaving."""
+    dev = _dev()
+    net = _net(lib, golden["unet_cond"])
+    g = torch.Generator().manual_seed(3)
+    lq = torch.rand(1, 3, 16, 16, generator=g).to(dev)
+    a, b = lib.IRSDE(10, 12, eps=0.005, device=dev), lib.IRSDE(30, 7, schedule="linear", eps=0.01, device=dev)
+    outs = {}
+    for name, sde in (("a", a), ("b", b), ("a2", a), ("b2", b)):
+        sde.set_model(net)
+        sde.set_mu(lq)
+        xT = lq + 0.1
+        zs = torch.randn(sde.T, 1, 3, 16, 16, generator=torch.Generator().manual_seed(5)).to(dev)
+        outs[name] = sde.reverse_posterior(xT, zs=zs)
+    assert torch.equal(outs["a"], outs["a2"]) and torch.equal(outs["b"], outs["b2"])
+    assert not torch.equal(outs["a"], outs["b"])
+    # and against the oracle, after the other sampler wrote last
+    u = golden["unet_cond"]
+    sc = O.Schedule(10, 12, "cosine", 0.005)
+    zs = torch.randn(12, 1, 3, 16, 16, generator=torch.Generator().manual_seed(5))
+    ref = O.reverse_chain(sc, lambda x, t: O.unet_forward(u["state"], x, lq.cpu(), t, u["nf"], u["depth"]), lq.cpu() + 0.1, lq.cpu(), zs,
+                          "posterior")
+    assert _maxdiff(outs["a2"], ref) < 1e-3
+
+
+def test_scalar_mu_before_set_mu(lib):
+    """IRSDE starts with mu = 0. (a float, sde_utils.py:88): the step functions broadcast it like the reference."""
+    dev = _dev()
+    sde = lib.IRSDE(10, 10, device=dev)
+    x = torch.rand(1, 3, 8, 8, device=dev)
+    score = torch.rand(1, 3, 8, 8, device=dev)
+    out = sde.reverse_ode_step(x, score, 5)
+    ref = x - (sde.thetas[5] * (0. - x) - 0.5 * sde.sigmas[5] ** 2 * score) * sde.dt.to(dev)
+    assert _maxdiff(out, ref) < 1e-6
+
+
+def test_plan_cache_is_bounded_and_trim(lib):
+    """A loop over variable-size images must not grow device memory without limit: the plan cache keeps at most
+    IRSDE_PLAN_CACHE_MAX (default 8) shapes; irsde_trim drops them all; results do not depend on cache state."""
+    dev = _dev()
+    torch.manual_seed(0)
+    net = lib.ConditionalUNet(3, 3, 8, depth=2).to(dev)
+    x = torch.rand(1, 3, 16, 16, device=dev)
+    first = net(x, x, 3)
+    ctx = net._ctx
+    sizes = []
+    for k in range(14):
+        h = 16 + 4 * k
+        net(torch.rand(1, 3, h, 20, device=dev), torch.rand(1, 3, h, 20, device=dev), 3)
+        sizes.append(int(ctx.L.irsde_device_bytes(ctx.h)))
+    assert sizes[-1] < sizes[7] * 2.5          # 14 ever-larger shapes, memory of <= 8 of them
+    lib._lib.check(ctx.L.irsde_trim(ctx.h), ctx.h)
+    assert int(ctx.L.irsde_device_bytes(ctx.h)) < sizes[0]
+    assert torch.equal(net(x, x, 3), first)

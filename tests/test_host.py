@@ -210,7 +210,7 @@ def test_state_dict_contract_nafnet_and_latent():
     (fixtures hold the reference modules' own state_dict), so `load_state_dict(strict=True)` of reference checkpoints works."""
     import irsde_b200
     gd = os.path.join(os.path.dirname(__file__), "golden")
-    naf = torch.load(os.path.join(gd, "reference_golden_nafnet.pt"), weights_only=False)
+    naf = torch.load(os.path.join(gd, "reference_golden_nafnet.pt"), weights_only=True)
     for key, g in naf.items():
         if not (isinstance(g, dict) and "state" in g):
             continue
@@ -218,7 +218,7 @@ def test_state_dict_contract_nafnet_and_latent():
         assert list(net.state_dict().keys()) == list(g["state"].keys()), key
         assert all(tuple(net.state_dict()[k].shape) == tuple(v.shape) for k, v in g["state"].items())
         net.load_state_dict(g["state"], strict=True)
-    lat = torch.load(os.path.join(gd, "reference_golden_latent.pt"), weights_only=False)
+    lat = torch.load(os.path.join(gd, "reference_golden_latent.pt"), weights_only=True)
     ae = irsde_b200.UNet(**lat["cfg"])
     assert list(ae.state_dict().keys()) == list(lat["state"].keys())
     ae.load_state_dict(lat["state"], strict=True)

@@ -99,7 +99,7 @@ def test_dsde_chain(golden):
 
 def test_nafnet_oracle_vs_reference():
     import os
-    g_all = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_nafnet.pt"), weights_only=False)
+    g_all = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_nafnet.pt"), weights_only=True)
     for key, g in g_all.items():
         c = g["cfg"]
         args = (c["width"], c["enc_blk_nums"], c["middle_blk_num"], c["dec_blk_nums"])
@@ -113,7 +113,7 @@ def test_nafnet_oracle_vs_reference():
 
 def test_latent_unet_oracle_vs_reference():
     import os
-    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_latent.pt"), weights_only=False)
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_latent.pt"), weights_only=True)
     c = g["cfg"]
     z, h = O.latent_unet_encode(g["state"], g["x"], c["ch_mult"])
     _close(z, g["z"], 1e-5)
