@@ -13,9 +13,10 @@ from .latent import UNet, latent_unet_param_shapes
 from . import imaging
 from .imaging import tensor2img, calculate_psnr, calculate_ssim
 from .pipeline import Restorer, plan_batches
+from .refusion import TiledRefusion, tile_boxes, plan_units
 from .dist import shard_range, sharded_reverse, broadcast_weights, NativeComm, comm_unique_id
 
 __all__ = ["IRSDE", "DenoisingSDE", "ConditionalUNet", "DenoisingUNet", "ConditionalNAFNet", "UNet", "unet_param_shapes", "latent_unet_param_shapes",
            "nafnet_param_shapes", "shard_range",
-           "sharded_reverse", "broadcast_weights", "NativeComm", "comm_unique_id", "imaging", "Restorer", "plan_batches", "tensor2img", "calculate_psnr", "calculate_ssim", "_lib"]
+           "sharded_reverse", "broadcast_weights", "NativeComm", "comm_unique_id", "TiledRefusion", "tile_boxes", "plan_units", "imaging", "Restorer", "plan_batches", "tensor2img", "calculate_psnr", "calculate_ssim", "_lib"]
 __version__ = "0.1"

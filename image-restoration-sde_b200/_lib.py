@@ -13,20 +13,21 @@ PREC_FP32, PREC_BF16 = 0, 1
 NET_CONDITIONAL, NET_DENOISING = 0, 1
 MODE_SDE, MODE_ODE, MODE_POSTERIOR, MODE_DSDE_SDE, MODE_DSDE_ODE = range(5)
 NUM_COEF = 8
+FLAG_FORCE_SIMT = 1   # irsde_config.flags: bf16 storage through the SIMT conv engine (debug aid)
 
 # every symbol include/irsde_b200.h declares
-SYMBOLS = ["irsde_create", "irsde_create_nafnet", "irsde_create_latent_unet", "irsde_latent_shape", "irsde_latent_encode",
+SYMBOLS = ["irsde_create", "irsde_create_ch_mult", "irsde_create_nafnet", "irsde_create_latent_unet", "irsde_latent_shape", "irsde_latent_encode",
            "irsde_latent_decode", "irsde_tensor2img_u8", "irsde_img2tensor_u8", "irsde_sqerr_u8", "irsde_ssim_workspace", "irsde_ssim_u8", "irsde_destroy", "irsde_last_error", "irsde_version", "irsde_load_tensor",
            "irsde_finalize_weights", "irsde_set_schedule", "irsde_set_coeffs", "irsde_noise_fn", "irsde_step",
            "irsde_reverse", "irsde_noise_state", "irsde_noise_state_images", "irsde_set_image_base", "irsde_set_image_uids", "irsde_comm_unique_id", "irsde_comm_init", "irsde_broadcast_weights", "irsde_gather", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
-           "irsde_profile_end", "irsde_conv2d_ex", "irsde_plan_num_ops", "irsde_plan_op_info", "irsde_trace_forward",
+           "irsde_profile_end", "irsde_profile_end_bytes", "irsde_conv2d_ex", "irsde_plan_num_ops", "irsde_plan_op_info", "irsde_trace_forward",
            "irsde_trim"]
 
 
 class Config(ctypes.Structure):
     _fields_ = [("in_nc", ctypes.c_int32), ("out_nc", ctypes.c_int32), ("nf", ctypes.c_int32),
                 ("depth", ctypes.c_int32), ("variant", ctypes.c_int32), ("precision", ctypes.c_int32),
-                ("device", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("device", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 _lib = None
@@ -44,6 +45,8 @@ def load():
     vp, i32, i64, u64, fp = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_float)
     L.irsde_create.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(vp)]
     L.irsde_create.restype = ctypes.c_int
+    L.irsde_create_ch_mult.argtypes = [ctypes.POINTER(Config), ctypes.POINTER(i32), i32, ctypes.POINTER(vp)]
+    L.irsde_create_ch_mult.restype = ctypes.c_int
     L.irsde_destroy.argtypes = [vp]
     L.irsde_destroy.restype = None
     L.irsde_last_error.argtypes = [vp]
@@ -101,6 +104,9 @@ def load():
     L.irsde_profile_end.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                     ctypes.POINTER(i64), i32]
     L.irsde_profile_end.restype = ctypes.c_int
+    L.irsde_profile_end_bytes.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                          ctypes.POINTER(i64), ctypes.POINTER(ctypes.c_double), i32]
+    L.irsde_profile_end_bytes.restype = ctypes.c_int
     _lib = L
     return L
 
@@ -123,11 +129,15 @@ def float_array(seq):
 class Context:
     """Owns one ``irsde_ctx`` (one per model per device)."""
 
-    def __init__(self, in_nc, out_nc, nf, depth, variant, precision, device_index, force_simt=False):
+    def __init__(self, in_nc, out_nc, nf, depth, variant, precision, device_index, force_simt=False, ch_mult=None):
         L = load()
-        cfg = Config(in_nc, out_nc, nf, depth, variant, precision, device_index, 1 if force_simt else 0)
+        cfg = Config(in_nc, out_nc, nf, depth, variant, precision, device_index, FLAG_FORCE_SIMT if force_simt else 0)
         h = ctypes.c_void_p()
-        check(L.irsde_create(ctypes.byref(cfg), ctypes.byref(h)))
+        if ch_mult is not None:
+            arr = (ctypes.c_int32 * len(ch_mult))(*ch_mult)
+            check(L.irsde_create_ch_mult(ctypes.byref(cfg), arr, len(ch_mult), ctypes.byref(h)))
+        else:
+            check(L.irsde_create(ctypes.byref(cfg), ctypes.byref(h)))
         self.h = h
         self.L = L
 

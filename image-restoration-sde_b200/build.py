@@ -39,6 +39,13 @@ def _write_build_info():
                                     text=True).stdout.strip())
     except Exception:
         commit, dirty = "", False
+    if not commit:  # no git here (the GPU box ships without .git): keep the commit recorded when the library was built
+        try:
+            for line in open(os.path.join(HERE, "BUILD_INFO")):
+                if line.startswith("commit="):
+                    commit, dirty = line.strip()[7:].replace("+dirty", ""), "+dirty" in line
+        except Exception:
+            pass
     with open(os.path.join(HERE, "BUILD_INFO"), "w") as f:
         f.write("commit=%s%s\ncsrc_sha256=%s\n" % (commit or "unknown", "+dirty" if dirty else "", csrc_sha256()))
 

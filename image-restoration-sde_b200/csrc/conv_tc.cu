@@ -46,6 +46,8 @@ struct TcParams {
   int tma_store;        // persistent kernel: bf16 NHWC output through smem + TMA bulk store
   int qsm;              // LinearAttention q: softmax over each 32-channel head * 32^-0.5 for output channels < 128
   int w_per_image;      // weights tensor is [B][Cout][Cin]: third TMA coordinate = image index
+  int n_fast;           // tile order: N tiles of one M tile are consecutive (1x1 convs with several N tiles, see tc_conv_create)
+  int tiles_n;
   int rows_a_bytes;     // ROWS mode: bytes of one A box ((BH+2) x BW x 128)
   unsigned long long* dbg;  // optional [grid][8] cycle counters (IRSDE_TC_DEBUG=1)
   const bf16* res;
@@ -435,8 +437,9 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, int tiles_m, int BN) {
   TileCoord t;
-  int m_idx = tile % tiles_m;
-  t.n0 = (tile / tiles_m) * BN;
+  int m_idx;
+  if (P.n_fast) { m_idx = tile / P.tiles_n; t.n0 = (tile - m_idx * P.tiles_n) * BN; }
+  else { m_idx = tile % tiles_m; t.n0 = (tile / tiles_m) * BN; }
   const int tw_i = m_idx % P.tilesW; m_idx /= P.tilesW;
   const int th_i = m_idx % P.tilesH; m_idx /= P.tilesH;
   t.b = m_idx % P.B;
@@ -969,6 +972,15 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
   d->tiles_m = P.tilesW * P.tilesH * B * nphases;
   d->num_tiles = d->tiles_m * ((Cout + BN - 1) / BN);
+  // Tile order.  Default: M fastest - the CTAs of a wave share one N tile, i.e. one set of weight tiles (3x3 layers: the
+  // weights of an N tile are MBs, the A tensor of the deep levels fits in L2).  1x1 convs with several N tiles (to_qkv:
+  // 384 outputs = 3 tiles) invert that: their weights are a few KB but the A tensor of the 256^2 / 128^2 levels is larger
+  // than L2, and M-fastest re-read it from DRAM once per N tile (ncu r02: 403 MB read for a 134 MB input).  N fastest
+  // makes the N tiles of one pixel tile run back to back in the same wave, so the second and third read hit L2.
+  P.tiles_n = (Cout + BN - 1) / BN;
+  // (only where the input is too large to stay in L2 anyway; small inputs keep M-fastest and its once-per-N-tile epilogue table)
+  const long long a_bytes = (long long)B * Hin * Win * in_pitch * 2;
+  P.n_fast = (ntaps == 1 && P.tiles_n > 1 && !P.w_per_image && a_bytes > (24ll << 20)) ? 1 : 0;
   // A: [planes][B][H][W][C] (C contiguous, pixel pitch in_pitch)
   {
     cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B, (cuuint64_t)planes};

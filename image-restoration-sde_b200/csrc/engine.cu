@@ -130,6 +130,7 @@ struct irsde_ctx {
   struct ProfEv { int cat; double flops; cudaEvent_t e0, e1; const OpRec* op; };
   std::vector<ProfEv> prof_events;
   bool use_tc = false;  // bf16 mode: route eligible convs through the tcgen05 engine
+  std::vector<int> udim;  // UNet channels per level: nf * [1, ch_mult...] (DenoisingUNet_arch.py:51-56)
 };
 
 namespace {
@@ -236,19 +237,20 @@ struct ResBlockInfo {
   std::string pre;
   int cin, cout;
 };
-std::vector<ResBlockInfo> resblocks(const irsde_config& c) {
+// D[i] = channels of level i: nf * [1, ch_mult...][i] (nf * 2^i for the plain depth constructor)
+std::vector<ResBlockInfo> resblocks(const irsde_config& c, const std::vector<int>& D) {
   std::vector<ResBlockInfo> v;
   char b[64];
   for (int i = 0; i < c.depth; ++i) {
-    int di = c.nf << i;
+    int di = D[i];
     snprintf(b, sizeof b, "downs.%d.0.", i); v.push_back({b, di, di});
     snprintf(b, sizeof b, "downs.%d.1.", i); v.push_back({b, di, di});
   }
-  int mid = c.nf << c.depth;
+  int mid = D[c.depth];
   v.push_back({"mid_block1.", mid, mid});
   v.push_back({"mid_block2.", mid, mid});
   for (int j = 0; j < c.depth; ++j) {
-    int i = c.depth - 1 - j, di = c.nf << i, dout = c.nf << (i + 1);
+    int i = c.depth - 1 - j, di = D[i], dout = D[i + 1];
     snprintf(b, sizeof b, "ups.%d.0.", j); v.push_back({b, dout + di, dout});
     snprintf(b, sizeof b, "ups.%d.1.", j); v.push_back({b, dout + di, dout});
   }
@@ -330,7 +332,7 @@ std::vector<ParamSpec> naf_param_specs(const NafCfg& n) {
   }
   return v;
 }
-std::vector<ParamSpec> param_specs(const irsde_config& c) {
+std::vector<ParamSpec> param_specs(const irsde_config& c, const std::vector<int>& D) {
   std::vector<ParamSpec> v;
   int64_t nf = c.nf, td = 4 * nf;
   int64_t cin0 = c.variant == IRSDE_NET_CONDITIONAL ? 2 * c.in_nc : c.in_nc;
@@ -339,7 +341,7 @@ std::vector<ParamSpec> param_specs(const irsde_config& c) {
   v.push_back({"time_mlp.1.bias", {td}});
   v.push_back({"time_mlp.3.weight", {td, td}});
   v.push_back({"time_mlp.3.bias", {td}});
-  for (auto& rb : resblocks(c)) {
+  for (auto& rb : resblocks(c, D)) {
     v.push_back({rb.pre + "mlp.1.weight", {2 * rb.cout, td}});
     v.push_back({rb.pre + "mlp.1.bias", {2 * rb.cout}});
     v.push_back({rb.pre + "block1.proj.weight", {rb.cout, rb.cin, 3, 3}});
@@ -360,7 +362,7 @@ std::vector<ParamSpec> param_specs(const irsde_config& c) {
   };
   char b[64];
   for (int i = 0; i < c.depth; ++i) {
-    int64_t di = nf << i, dout = nf << (i + 1);
+    int64_t di = D[i], dout = D[i + 1];
     snprintf(b, sizeof b, "downs.%d.2.", i);
     attn(b, di, false);
     snprintf(b, sizeof b, "downs.%d.3.", i);
@@ -371,10 +373,10 @@ std::vector<ParamSpec> param_specs(const irsde_config& c) {
       v.push_back({std::string(b) + "weight", {dout, di, 3, 3}});
     }
   }
-  attn("mid_attn.", nf << c.depth, c.variant == IRSDE_NET_DENOISING);
+  attn("mid_attn.", D[c.depth], c.variant == IRSDE_NET_DENOISING);
   for (int j = 0; j < c.depth; ++j) {
     int i = c.depth - 1 - j;
-    int64_t di = nf << i, dout = nf << (i + 1);
+    int64_t di = D[i], dout = D[i + 1];
     snprintf(b, sizeof b, "ups.%d.2.", j);
     attn(b, dout, false);
     if (i != 0) {
@@ -1005,6 +1007,7 @@ struct Builder {
   void build() {
     const irsde_config& c = ctx->cfg;
     int B = plan->B, nf = c.nf, depth = c.depth;
+    const std::vector<int>& D = ctx->udim;
     int s = 1 << depth;
     plan->Hp = plan->H + (s - plan->H % s) % s;
     plan->Wp = plan->W + (s - plan->W % s) % s;
@@ -1038,7 +1041,7 @@ struct Builder {
     std::vector<T*> U1(depth), U2(depth);
     char nb[64];
     for (int i = 0; i < depth; ++i) {
-      int di = nf << i, dout = nf << (i + 1), H = hs[i], W = ws[i];
+      int di = D[i], dout = D[i + 1], H = hs[i], W = ws[i];
       long long npix = (long long)B * H * W;
       U1[i] = alloc(npix * (dout + di));
       U2[i] = alloc(npix * (dout + di));
@@ -1062,7 +1065,7 @@ struct Builder {
       }
     }
     {
-      int i = depth - 1, di = nf << i, mid = nf << depth, H = hs[i], W = ws[i];
+      int i = depth - 1, di = D[i], mid = D[depth], H = hs[i], W = ws[i];
       long long npix = (long long)B * H * W;
       T* m1 = tmp(npix * mid);
       T* m2 = tmp(npix * mid);
@@ -1073,7 +1076,7 @@ struct Builder {
       release(m2);
     }
     for (int j = 0; j < depth; ++j) {
-      int i = depth - 1 - j, di = nf << i, dout = nf << (i + 1), H = hs[i], W = ws[i];
+      int i = depth - 1 - j, di = D[i], dout = D[i + 1], H = hs[i], W = ws[i];
       long long npix = (long long)B * H * W;
       snprintf(nb, sizeof nb, "ups.%d.", j);
       std::string pre = nb;
@@ -1084,10 +1087,10 @@ struct Builder {
       attention(pre + "2.", V{tb, dout, dout}, V{tc, dout, dout}, H, W, false, la_partial, la_ctx);
       release(tb);
       if (i != 0) {
-        int dprev = nf << i;  // == dout of level i-1
+        int dprev = D[i];  // == dout of level i-1
         std::string bn = pre + "3.1.bias";
         conv(pre + "3.1.weight", V{tc, dout, dout}, H, W, 3, 1, 1, 2, bn.c_str(), "", 0, nullptr,
-             view(U1[i - 1], dprev + (nf << (i - 1)), 0, dprev), di);
+             view(U1[i - 1], dprev + D[i - 1], 0, dprev), di);
       } else {
         conv(pre + "3.weight", V{tc, dout, dout}, H, W, 3, 1, 1, 1, nullptr, "", 0, nullptr, view(F, 2 * nf, 0, nf), di);
       }
@@ -1326,8 +1329,22 @@ int irsde_create(const irsde_config* cfg, irsde_ctx** out) {
     delete c;
     return fail(nullptr, IRSDE_ERR_CUDA, "tensor-core engine init failed: " + terr);
   }
-  c->use_tc = cfg->precision == IRSDE_PREC_BF16 && !(cfg->reserved & 1);  // reserved bit0: force SIMT (debug)
+  c->use_tc = cfg->precision == IRSDE_PREC_BF16 && !(cfg->flags & IRSDE_FLAG_FORCE_SIMT);
+  for (int i = 0; i <= cfg->depth; ++i) c->udim.push_back(cfg->nf * (1 << i));
   *out = c;
+  return IRSDE_OK;
+}
+
+int irsde_create_ch_mult(const irsde_config* cfg, const int32_t* ch_mult, int32_t n_levels, irsde_ctx** out) {
+  if (!cfg || !ch_mult || !out || n_levels < 1 || n_levels > 6) return fail(nullptr, IRSDE_ERR_INVALID, "bad ch_mult");
+  for (int i = 0; i < n_levels; ++i)
+    if (ch_mult[i] < 1 || (long long)ch_mult[i] * cfg->nf > 65536) return fail(nullptr, IRSDE_ERR_INVALID, "bad ch_mult entry");
+  irsde_config c2 = *cfg;
+  c2.depth = n_levels;
+  int rc = irsde_create(&c2, out);
+  if (rc) return rc;
+  (*out)->udim.assign(1, cfg->nf);
+  for (int i = 0; i < n_levels; ++i) (*out)->udim.push_back(cfg->nf * ch_mult[i]);
   return IRSDE_OK;
 }
 
@@ -1338,7 +1355,7 @@ int irsde_create_latent_unet(const irsde_latent_unet_config* lcfg, irsde_ctx** o
   irsde_config cfg;
   memset(&cfg, 0, sizeof cfg);
   cfg.in_nc = lcfg->in_ch; cfg.out_nc = lcfg->out_ch; cfg.nf = 8; cfg.depth = lcfg->n_levels;
-  cfg.variant = IRSDE_NET_CONDITIONAL; cfg.precision = lcfg->precision; cfg.device = lcfg->device; cfg.reserved = lcfg->reserved;
+  cfg.variant = IRSDE_NET_CONDITIONAL; cfg.precision = lcfg->precision; cfg.device = lcfg->device; cfg.flags = lcfg->flags;
   int rc = irsde_create(&cfg, out);
   if (rc) return rc;
   irsde_ctx* c = *out;
@@ -1397,7 +1414,7 @@ int irsde_create_nafnet(const irsde_nafnet_config* ncfg, irsde_ctx** out) {
   cfg.variant = IRSDE_NET_CONDITIONAL;
   cfg.precision = ncfg->precision;
   cfg.device = ncfg->device;
-  cfg.reserved = ncfg->reserved;
+  cfg.flags = ncfg->flags;
   int rc = irsde_create(&cfg, out);
   if (rc) return rc;
   irsde_ctx* c = *out;
@@ -1557,7 +1574,7 @@ int irsde_load_tensor(irsde_ctx* ctx, const char* name, const void* data, int32_
 int irsde_finalize_weights(irsde_ctx* ctx) {
   if (!ctx) return fail(nullptr, IRSDE_ERR_INVALID, "null ctx");
   cudaSetDevice(ctx->cfg.device);
-  auto specs = ctx->lat.on ? lat_param_specs(ctx->lat) : (ctx->naf.on ? naf_param_specs(ctx->naf) : param_specs(ctx->cfg));
+  auto specs = ctx->lat.on ? lat_param_specs(ctx->lat) : (ctx->naf.on ? naf_param_specs(ctx->naf) : param_specs(ctx->cfg, ctx->udim));
   for (auto& s : specs) {
     auto it = ctx->raw.find(s.name);
     if (it == ctx->raw.end()) return fail(ctx, IRSDE_ERR_STATE, "missing state-dict entry " + s.name);
@@ -1607,7 +1624,7 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
     for (auto& b : naf_blocks(ctx->naf)) tbs.push_back({b.pre, 4 * b.c});
   } else {
     td = ctx->cfg.nf * 4;
-    for (auto& rb : resblocks(ctx->cfg)) tbs.push_back({rb.pre, 2 * rb.cout});
+    for (auto& rb : resblocks(ctx->cfg, ctx->udim)) tbs.push_back({rb.pre, 2 * rb.cout});
   }
   int S = 0;
   for (auto& t : tbs) { ctx->ss_off[t.pre] = S; S += t.rows; }
@@ -1813,11 +1830,15 @@ int irsde_profile_begin(irsde_ctx* ctx) {
 }
 
 int irsde_profile_end(irsde_ctx* ctx, double* ms, double* flops, int64_t* launches, int32_t ncat) {
+  return irsde_profile_end_bytes(ctx, ms, flops, launches, nullptr, ncat);
+}
+
+int irsde_profile_end_bytes(irsde_ctx* ctx, double* ms, double* flops, int64_t* launches, double* bytes, int32_t ncat) {
   if (!ctx || !ms || !flops || !launches || ncat < CAT_COUNT) return fail(ctx, IRSDE_ERR_INVALID, "bad argument");
   cudaSetDevice(ctx->cfg.device);
   ctx->prof = false;
   CUDA_TRY(ctx, cudaDeviceSynchronize());
-  for (int i = 0; i < ncat; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; }
+  for (int i = 0; i < ncat; ++i) { ms[i] = 0; flops[i] = 0; launches[i] = 0; if (bytes) bytes[i] = 0; }
   const char* dump = getenv("IRSDE_PROFILE_DUMP");
   for (auto& e : ctx->prof_events) {
     float t = 0.f;
@@ -1826,6 +1847,7 @@ int irsde_profile_end(irsde_ctx* ctx, double* ms, double* flops, int64_t* launch
       fprintf(stderr, "PROF\t%d\t%.4f\t%.1f\t%.1f\t%s\n", e.cat, t, e.op->flops > 0 ? e.op->flops / (t * 1e-3) / 1e12 : 0.0,
               e.op->bytes > 0 ? e.op->bytes / (t * 1e-3) / 1e9 : 0.0, e.op->label.c_str());
     ms[e.cat] += t;
+    if (bytes && e.op) bytes[e.cat] += e.op->bytes;
     flops[e.cat] += e.flops;
     launches[e.cat] += 1;
     cudaEventDestroy(e.e0);

@@ -69,7 +69,7 @@ def latent_unet_param_shapes(in_ch, out_ch, ch, ch_mult, embed_dim):
 class _LatConfig(ctypes.Structure):
     _fields_ = [("in_ch", ctypes.c_int32), ("out_ch", ctypes.c_int32), ("ch", ctypes.c_int32), ("n_levels", ctypes.c_int32),
                 ("ch_mult", ctypes.c_int32 * 8), ("embed_dim", ctypes.c_int32), ("precision", ctypes.c_int32),
-                ("device", ctypes.c_int32), ("reserved", ctypes.c_int32)]
+                ("device", ctypes.c_int32), ("flags", ctypes.c_int32)]
 
 
 class _LatContext(_lib.Context):

@@ -64,7 +64,7 @@ class _NafConfig(ctypes.Structure):
     _fields_ = [("img_channel", ctypes.c_int32), ("width", ctypes.c_int32), ("middle_blk_num", ctypes.c_int32),
                 ("n_levels", ctypes.c_int32), ("enc_blk_nums", ctypes.c_int32 * 8), ("dec_blk_nums", ctypes.c_int32 * 8),
                 ("latent", ctypes.c_int32), ("precision", ctypes.c_int32), ("device", ctypes.c_int32),
-                ("reserved", ctypes.c_int32)]
+                ("flags", ctypes.c_int32)]
 
 
 class _NafContext(_lib.Context):

@@ -15,7 +15,13 @@ What it does before handing control to the script (nothing in the reference tree
     (IPython.embed, lpips.LPIPS, lmdb, ema_pytorch.EMA) - only when the real ones are not importable.
 
 Precision / graph / RNG knobs come from the environment so existing YAMLs still parse:
-IRSDE_B200_PRECISION=fp32|bf16, IRSDE_B200_GRAPH=0|1, IRSDE_B200_RNG=torch|philox.
+IRSDE_B200_PRECISION=fp32|bf16|fp32x3, IRSDE_B200_GRAPH=0|1, IRSDE_B200_RNG=torch|philox.
+
+Two launcher options (before the script path) exist for A/B parity runs (tests/test_gpu_dropin.py):
+  --seed N       torch.manual_seed(N) right before the script starts (test.py never seeds: noise_state and the per-step
+                 randn_like draws are otherwise irreproducible);
+  --reference    do NOT swap anything: only the stand-ins for missing optional modules and the seed, i.e. the unmodified
+                 reference on its own PyTorch path - the other arm of the comparison.
 """
 import importlib
 import inspect
@@ -101,12 +107,31 @@ def install(script_dir):
 
 def main(argv=None):
     argv = list(sys.argv[1:] if argv is None else argv)
+    seed, reference = None, False
+    while argv and argv[0].startswith("--"):
+        opt = argv.pop(0)
+        if opt == "--seed":
+            seed = int(argv.pop(0))
+        elif opt == "--reference":
+            reference = True
+        else:
+            raise SystemExit("unknown launcher option %s\n%s" % (opt, __doc__))
     if not argv:
         raise SystemExit(__doc__)
     script = os.path.abspath(argv[0])
     script_dir = os.path.dirname(script)
     os.chdir(script_dir)
-    install(script_dir)
+    if reference:
+        codes = os.path.abspath(os.path.join(script_dir, "..", ".."))
+        for p in (script_dir, codes):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        _stub_missing()
+    else:
+        install(script_dir)
+    if seed is not None:
+        import torch
+        torch.manual_seed(seed)
     sys.argv = [script] + argv[1:]
     runpy.run_path(script, run_name="__main__")
 

@@ -12,9 +12,12 @@ import torch.nn as nn
 from . import _lib
 
 
-def unet_param_shapes(in_nc, out_nc, nf, depth, variant="conditional"):
+def unet_param_shapes(in_nc, out_nc, nf, depth, variant="conditional", ch_mult=None):
     """State-dict entries in the reference's registration order
-    (DenoisingUNet_arch.py:27-76; module_util.py:125-161,185-190)."""
+    (DenoisingUNet_arch.py:27-76; module_util.py:125-161,185-190).  ``ch_mult`` selects the latent-task variant
+    (latent-dehazing/.../DenoisingUNet_arch.py:20,51-56): level i has nf*[1,ch_mult...][i] channels."""
+    mult = [1] + list(ch_mult) if ch_mult is not None else [2 ** i for i in range(depth + 1)]
+    depth = len(mult) - 1
     S = {}
     td = nf * 4
     S["init_conv.weight"] = (nf, in_nc * 2 if variant == "conditional" else in_nc, 7, 7)
@@ -44,7 +47,7 @@ def unet_param_shapes(in_nc, out_nc, nf, depth, variant="conditional"):
 
     ups = []
     for i in range(depth):
-        di, do = nf * 2 ** i, nf * 2 ** (i + 1)
+        di, do = nf * mult[i], nf * mult[i + 1]
         pre = "downs.%d." % i
         rb(pre + "0.", di, di)
         rb(pre + "1.", di, di)
@@ -65,7 +68,7 @@ def unet_param_shapes(in_nc, out_nc, nf, depth, variant="conditional"):
             S[pre + "3.1.bias"] = (di,)
         else:
             S[pre + "3.weight"] = (di, do, 3, 3)
-    mid = nf * 2 ** depth
+    mid = nf * mult[depth]
     rb("mid_block1.", mid, mid)
     attn("mid_attn.", mid, full=(variant != "conditional"))
     rb("mid_block2.", mid, mid)
@@ -86,15 +89,21 @@ class ConditionalUNet(nn.Module):
 
     variant = "conditional"
 
-    def __init__(self, in_nc, out_nc, nf, depth=4, upscale=1, precision=None, force_simt=False):
+    def __init__(self, in_nc, out_nc, nf, depth=4, upscale=1, precision=None, force_simt=False, ch_mult=None):
         super().__init__()
         import os
+        if isinstance(depth, (list, tuple)):   # latent-task signature: ConditionalUNet(in_nc, out_nc, nf, ch_mult)
+            ch_mult, depth = list(depth), len(depth)
+        if ch_mult is not None:
+            ch_mult = [int(m) for m in ch_mult]
+            depth = len(ch_mult)
+        self.ch_mult = ch_mult
         self.in_nc, self.out_nc, self.nf, self.depth, self.upscale = in_nc, out_nc, nf, depth, upscale
         self.precision = precision or os.environ.get("IRSDE_B200_PRECISION", "fp32")
         if self.precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         self._force_simt = force_simt
-        self._shapes = unet_param_shapes(in_nc, out_nc, nf, depth, self.variant)
+        self._shapes = unet_param_shapes(in_nc, out_nc, nf, depth, self.variant, ch_mult)
         for name, shp in self._shapes.items():
             parts = name.split(".")
             node = self
@@ -132,7 +141,7 @@ class ConditionalUNet(nn.Module):
             self._ctx = _lib.Context(self.in_nc, self.out_nc, self.nf, self.depth,
                                      _lib.NET_CONDITIONAL if self.variant == "conditional" else _lib.NET_DENOISING,
                                      _lib.PREC_FP32 if self.precision == "fp32" else _lib.PREC_BF16, idx,
-                                     force_simt=self._force_simt)
+                                     force_simt=self._force_simt, ch_mult=self.ch_mult)
             self._ctx_dev = idx
             self._sig = None
         return self._ctx

@@ -59,8 +59,11 @@ typedef struct {
   int32_t variant;   /* IRSDE_NET_*                              */
   int32_t precision; /* IRSDE_PREC_*                             */
   int32_t device;    /* CUDA device ordinal                      */
-  int32_t reserved;
+  int32_t flags;     /* IRSDE_FLAG_* (0 = defaults)              */
 } irsde_config;
+/* flags (all three config structs): bf16 storage through the fp32-FMA SIMT conv engine instead of tcgen05 - a debugging
+ * aid that separates storage rounding from tensor-core issues; never the product path. */
+#define IRSDE_FLAG_FORCE_SIMT 1
 
 /* Refusion score network: ConditionalNAFNet(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums)
  * (codes/config/deraining/models/modules/DenoisingNAFNet_arch.py:87-143); latent != 0 selects the latent
@@ -75,7 +78,7 @@ typedef struct {
   int32_t latent;
   int32_t precision;         /* IRSDE_PREC_* */
   int32_t device;
-  int32_t reserved;
+  int32_t flags;             /* IRSDE_FLAG_* */
 } irsde_nafnet_config;
 
 /* Refusion latent autoencoder: UNet(in_ch, out_ch, ch, ch_mult, embed_dim)
@@ -87,12 +90,16 @@ typedef struct {
   int32_t embed_dim;
   int32_t precision;     /* IRSDE_PREC_* */
   int32_t device;
-  int32_t reserved;
+  int32_t flags;         /* IRSDE_FLAG_* */
 } irsde_latent_unet_config;
 
 /* Replaces `ConditionalUNet(in_nc,out_nc,nf,depth)` + `.to(device)`
  * (DenoisingUNet_arch.py:20, models/denoising_model.py:36). */
 int irsde_create(const irsde_config* cfg, irsde_ctx** out);
+/* The latent-task variant `ConditionalUNet(in_nc, out_nc, nf, ch_mult=[1,2,4,4])`
+ * (codes/config/latent-dehazing/models/modules/DenoisingUNet_arch.py:17-20,51-56,70): level i has nf*[1,ch_mult...][i]
+ * channels and depth = len(ch_mult) (cfg->depth is ignored). */
+int irsde_create_ch_mult(const irsde_config* cfg, const int32_t* ch_mult, int32_t n_levels, irsde_ctx** out);
 /* Same context type, ConditionalNAFNet architecture; every other entry point (load_tensor, noise_fn, reverse, ...)
  * is shared.  Replaces `ConditionalNAFNet(...)` + `.to(device)` (DenoisingNAFNet_arch.py:89). */
 int irsde_create_nafnet(const irsde_nafnet_config* cfg, irsde_ctx** out);
@@ -165,6 +172,9 @@ int irsde_set_image_uids(irsde_ctx* ctx, const uint64_t* uids, int32_t n, void* 
  * ms, the executed conv flops and the number of ops.  ncat must be >= 6. */
 int irsde_profile_begin(irsde_ctx* ctx);
 int irsde_profile_end(irsde_ctx* ctx, double* ms, double* flops, int64_t* launches, int32_t ncat);
+/* Same, plus bytes[cat] = the ops' ALGORITHMIC HBM bytes (each op's inputs + outputs + its weights once):
+ * the numerator of the HBM roofline of the memory-bound kernels. */
+int irsde_profile_end_bytes(irsde_ctx* ctx, double* ms, double* flops, int64_t* launches, double* bytes, int32_t ncat);
 
 /* Kernel launches issued by this context since creation (for bench.py's gpu_launches). */
 int64_t irsde_launch_count(const irsde_ctx* ctx);

@@ -238,6 +238,10 @@ def full_attention(P, pre, x, heads=4, dim_head=32, trace=None):
 
 
 def unet_forward(P, xt, cond, time, nf, depth, variant="conditional", trace=None):
+    # `depth` may be the latent-task variant's ch_mult list (latent-dehazing/.../DenoisingUNet_arch.py:20): the forward
+    # is the same, only the number of levels (= len(ch_mult)) matters here - channel widths come from the weights
+    if isinstance(depth, (list, tuple)):
+        depth = len(depth)
     """ConditionalUNet.forward.  codes/config/deraining/models/modules/DenoisingUNet_arch.py:85-134
     (variant="conditional": input cat(xt-cond, cond)); the denoising-sde variant
     (codes/config/denoising-sde/models/modules/DenoisingUNet_arch.py:84-132) takes x only and
@@ -300,7 +304,10 @@ def unet_forward(P, xt, cond, time, nf, depth, variant="conditional", trace=None
 
 def unet_param_shapes(in_nc, out_nc, nf, depth, variant="conditional"):
     """State-dict names -> shapes, in the reference's registration order
-    (DenoisingUNet_arch.py:19-76, module_util.py:125-161,185-190)."""
+    (DenoisingUNet_arch.py:19-76, module_util.py:125-161,185-190).  `depth` may be a ch_mult list: the latent-task
+    variant (latent-dehazing/.../DenoisingUNet_arch.py:20,51-56,70) whose level i has nf*[1,ch_mult...][i] channels."""
+    mult = [1] + list(depth) if isinstance(depth, (list, tuple)) else [2 ** i for i in range(depth + 1)]
+    depth = len(mult) - 1
     S = {}
     td = nf * 4
     cin0 = in_nc * 2 if variant == "conditional" else in_nc
@@ -331,7 +338,7 @@ def unet_param_shapes(in_nc, out_nc, nf, depth, variant="conditional"):
 
     ups = []
     for i in range(depth):
-        di, do = nf * 2 ** i, nf * 2 ** (i + 1)
+        di, do = nf * mult[i], nf * mult[i + 1]
         pre = "downs.%d." % i
         rb(pre + "0.", di, di)
         rb(pre + "1.", di, di)
@@ -352,7 +359,7 @@ def unet_param_shapes(in_nc, out_nc, nf, depth, variant="conditional"):
             S[pre + "3.1.bias"] = (di,)
         else:
             S[pre + "3.weight"] = (di, do, 3, 3)
-    mid = nf * 2 ** depth
+    mid = nf * mult[depth]
     rb("mid_block1.", mid, mid)
     la("mid_attn.", mid, full=(variant != "conditional"))
     rb("mid_block2.", mid, mid)

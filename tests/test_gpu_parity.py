@@ -621,3 +621,18 @@ def test_plan_cache_is_bounded_and_trim(lib):
     lib._lib.check(ctx.L.irsde_trim(ctx.h), ctx.h)
     assert int(ctx.L.irsde_device_bytes(ctx.h)) < sizes[0]
     assert torch.equal(net(x, x, 3), first)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_ch_mult_variant(lib, precision):
+    """The latent tasks' ConditionalUNet(in_nc, out_nc, nf, ch_mult): fp32 <= 1e-4 vs the reference's own output."""
+    import os
+    dev = _dev()
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_chmult.pt"), weights_only=True)
+    c = g["cfg"]
+    net = lib.ConditionalUNet(c["in_nc"], c["out_nc"], c["nf"], ch_mult=c["ch_mult"], precision=precision)
+    net.load_state_dict(g["state"], strict=True)
+    net = net.to(dev)
+    tol = 1e-4 if precision == "fp32" else 4e-2 * g["y_int"].abs().max().item()
+    assert _maxdiff(net(g["x"].to(dev), g["cond"].to(dev), g["t_int"]), g["y_int"]) < tol
+    assert _maxdiff(net(g["x"].to(dev), g["cond"].to(dev), g["t_vec"]), g["y_vec"]) < tol

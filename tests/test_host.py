@@ -113,7 +113,8 @@ def _worker(rank, world, port, q):
             for p in lin.parameters():
                 p.zero_()
     irsde_b200.broadcast_weights(lin, src=0)
-    q.put((rank, out, torch.cat([p.detach().reshape(-1) for p in lin.parameters()])))
+    # numpy payloads are pickled by value; a tensor travels as a shared-memory fd that dies with this worker (flaky)
+    q.put((rank, out.numpy(), torch.cat([p.detach().reshape(-1) for p in lin.parameters()]).numpy()))
     dist.destroy_process_group()
 
 
@@ -127,6 +128,7 @@ def test_sharded_gather_gloo_world2():
     for p in ps:
         p.start()
     res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
+    res = [(r, torch.from_numpy(o), torch.from_numpy(w)) for r, o, w in res]
     for p in ps:
         p.join(60)
     xT = torch.arange(5 * 3 * 2 * 2, dtype=torch.float32).reshape(5, 3, 2, 2)
@@ -246,3 +248,78 @@ def test_front_end_needs_cuda():
         irsde_b200.Restorer(sde, device="cpu").restore([img])
     with pytest.raises(TypeError):
         irsde_b200.Restorer(sde, device="cpu").restore([img.astype(np.float32)])
+
+
+# ---- Refusion tile sharding: host logic (grid, grouping by shape, unit partition, gathers, stitching) on gloo ------------
+class _FakeAE:
+    """CPU stand-in for the latent autoencoder: 'encode' = 2x2 average pool of 4 channels, 'decode' = nearest upsample."""
+    def encode(self, x):
+        z = torch.nn.functional.avg_pool2d(torch.cat([x, x[:, :1]], 1), 2)
+        return z, ("skips", x.shape)
+
+    def decode(self, z, h):
+        assert h[0] == "skips" and h[1][0] == z.shape[0]
+        return torch.nn.functional.interpolate(z[:, :3], scale_factor=2, mode="nearest")
+
+
+def _fake_chain(mu, uids):   # depends on the tile content AND the unit's global uid AND the tile's own mean (a "global" op)
+    u = torch.tensor(uids, dtype=torch.float32)[:, None, None, None]
+    return mu * 2 + u + mu.mean(dim=(2, 3), keepdim=True)
+
+
+def _tile_worker(rank, world, port, q):
+    import torch.distributed as dist
+    import irsde_b200
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    LQ = torch.arange(3 * 3 * 20 * 28, dtype=torch.float32).reshape(3, 3, 20, 28) / 100.0
+    tr = irsde_b200.TiledRefusion(_FakeAE(), None, tile=4, chain=_fake_chain)   # latent 10x14 -> 3x4 grid, ragged edges
+    out, (lo, hi) = tr.restore(LQ)
+    q.put((rank, lo, hi, out.numpy()))   # numpy: pickled by value (a tensor's shared-memory fd dies with the worker)
+    dist.destroy_process_group()
+
+
+def test_tile_grid_and_units():
+    import irsde_b200
+    assert irsde_b200.tile_boxes(10, 14, 4) == [(y, min(y + 4, 10), x, min(x + 4, 14)) for y in (0, 4, 8) for x in (0, 4, 8, 12)]
+    assert irsde_b200.tile_boxes(10, 14, None) == [(0, 10, 0, 14)]
+    units, groups = irsde_b200.plan_units(2, 10, 14, 4)
+    assert [u[0] for u in units] == list(range(24)) and units[13][1] == 1
+    assert sorted(groups) == [(2, 2), (2, 4), (4, 2), (4, 4)]
+    assert sum(len(v) for v in groups.values()) == 24 and len(groups[(4, 4)]) == 12
+    cover = torch.zeros(10, 14)
+    for _, b, (y0, y1, x0, x1) in units[:12]:
+        cover[y0:y1, x0:x1] += 1
+    assert (cover == 1).all()           # tiles partition the latent: every pixel exactly once
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_tiled_refusion_gloo(world):
+    """world_size 2 and 4 (4 ranks > 3 images: one rank owns no image but still processes tiles): the sharded pipeline
+    reproduces the single-process result exactly, and that equals the per-tile definition computed by hand."""
+    import torch.multiprocessing as mp
+    import irsde_b200
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + world) % 2000
+    ps = [ctx.Process(target=_tile_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in ps], key=lambda r: r[0])
+    for p in ps:
+        p.join(60)
+    LQ = torch.arange(3 * 3 * 20 * 28, dtype=torch.float32).reshape(3, 3, 20, 28) / 100.0
+    single, _ = irsde_b200.TiledRefusion(_FakeAE(), None, tile=4, chain=_fake_chain).restore(LQ)
+    got = torch.cat([torch.from_numpy(r[3]) for r in res])
+    assert [(r[1], r[2]) for r in res] == [irsde_b200.shard_range(3, r, world) for r in range(world)]
+    assert torch.equal(got, single)
+    # by hand: every tile independently, uid = image * tiles_per_image + tile index
+    ae = _FakeAE()
+    z, h = ae.encode(LQ)
+    ref = torch.empty_like(z)
+    boxes = irsde_b200.tile_boxes(10, 14, 4)
+    for b in range(3):
+        for k, (y0, y1, x0, x1) in enumerate(boxes):
+            ref[b:b + 1, :, y0:y1, x0:x1] = _fake_chain(z[b:b + 1, :, y0:y1, x0:x1], [b * len(boxes) + k])
+    assert torch.allclose(single, ae.decode(ref, h), rtol=1e-6, atol=1e-4)   # batch-of-tiles vs one-tile reductions: last ulp

@@ -1,4 +1,5 @@
 """Pin the CPU oracle against outputs of the imported reference (tests/golden/make_golden.py)."""
+import os
 import torch
 
 from oracle import irsde_oracle as O
@@ -190,3 +191,23 @@ def test_imaging_oracle_matches_reference():
     assert abs(IO.calculate_ssim(g["x"], g["y"]) - float(g["ssim"])) < 1e-12
     assert abs(IO.calculate_ssim(g["x"][4:-4, 4:-4], g["y"][4:-4, 4:-4]) - float(g["ssim_crop4"])) < 1e-12
     assert abs(IO.calculate_ssim(g["x"][:, :, 0], g["y"][:, :, 0]) - float(g["ssim_gray"])) < 1e-12
+
+
+def test_unet_ch_mult_variant_vs_reference():
+    """ConditionalUNet(in_nc, out_nc, nf, ch_mult=[...]) of the latent tasks (latent-dehazing/.../DenoisingUNet_arch.py:20):
+    oracle and state-dict table against the reference's own output."""
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_chmult.pt"), weights_only=True)
+    c = g["cfg"]
+    shapes = O.unet_param_shapes(c["in_nc"], c["out_nc"], c["nf"], c["ch_mult"])
+    assert list(shapes.keys()) == list(g["state"].keys())
+    assert all(tuple(g["state"][k].shape) == tuple(v) for k, v in shapes.items())
+    y = O.unet_forward(g["state"], g["x"], g["cond"], g["t_int"], c["nf"], c["ch_mult"])
+    assert (y - g["y_int"]).abs().max().item() < 1e-5
+    y = O.unet_forward(g["state"], g["x"], g["cond"], g["t_vec"], c["nf"], c["ch_mult"])
+    assert (y - g["y_vec"]).abs().max().item() < 1e-5
+    import irsde_b200
+    m = irsde_b200.ConditionalUNet(c["in_nc"], c["out_nc"], c["nf"], ch_mult=c["ch_mult"])
+    assert list(m.state_dict().keys()) == list(g["state"].keys())
+    m.load_state_dict(g["state"], strict=True)
+    m2 = irsde_b200.ConditionalUNet(c["in_nc"], c["out_nc"], c["nf"], c["ch_mult"])   # positional, like the reference signature
+    assert m2.depth == 3 and list(m2.state_dict().keys()) == list(g["state"].keys())
