@@ -9,7 +9,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("IRSDE_B200_LIB") or os.path.join(HERE, "libirsde_b200.so")  # override: A/B of builds
 
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP32X3 = 0, 1, 2
+# name -> irsde_config.precision.  fp32: fp32 storage + SIMT FMA; bf16: tcgen05 bf16 (perf mode); fp32x3: fp32 storage,
+# every conv = 3 x tcgen05.mma.kind::tf32 on hi/lo split operands (tensor cores at the fp32 mode's accuracy)
+PRECISIONS = {"fp32": PREC_FP32, "bf16": PREC_BF16, "fp32x3": PREC_FP32X3}
 NET_CONDITIONAL, NET_DENOISING = 0, 1
 MODE_SDE, MODE_ODE, MODE_POSTERIOR, MODE_DSDE_SDE, MODE_DSDE_ODE = range(5)
 NUM_COEF = 8

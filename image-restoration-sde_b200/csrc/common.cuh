@@ -183,6 +183,12 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
                            int nphases /*1 or 4 (upsample phases)*/, const Epilogue& ep, bf16* out, int out_pitch,
                            int Hout, int Wout, std::string* err, int flags = 0);
 enum { TC_FLAG_QSOFTMAX = 1, TC_FLAG_W_PER_IMAGE = 2 };
+// fp32x3 mode (3 x tcgen05.mma.kind::tf32 on hi/lo split fp32 operands, fp32 output); see conv_tc.cu MODE 3
+TcConvDesc* tc_conv_create_f32x3(const float* in_split /*[2][planes][B][H][W][Cin]*/, int B, int Hin, int Win, int Cin, int planes,
+                                 const float* wsplit /*[phase*tap][2][Cout_w][Cin]*/, int Cout, int ntaps, const TcTap* taps,
+                                 int nphases, const Epilogue& ep, float* out, int out_pitch, int Hout, int Wout, std::string* err);
+// hi = rn_tf32(x), lo = rn_tf32(x - hi) of a pitched NHWC fp32 view -> dense out[0][npix][C] (hi), out[1][npix][C] (lo)
+void launch_split_tf32(const float* in, int in_pitch, float* out, long long npix, int C, cudaStream_t st);
 bool tc_fused_attention_available();
 void tc_conv_destroy(TcConvDesc*);
 void tc_conv_set_runtime(TcConvDesc*, const float* ss, const int* t_ptr, int ss_img_stride);

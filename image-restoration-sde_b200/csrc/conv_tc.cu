@@ -46,6 +46,9 @@ struct TcParams {
   int tma_store;        // persistent kernel: bf16 NHWC output through smem + TMA bulk store
   int qsm;              // LinearAttention q: softmax over each 32-channel head * 32^-0.5 for output channels < 128
   int w_per_image;      // weights tensor is [B][Cout][Cin]: third TMA coordinate = image index
+  float* out_f32;       // MODE 3 (fp32x3): fp32 NHWC output view (channel offset applied), pitch = out_pitch
+  const float* res_f32; // MODE 3: fp32 residual view
+  int lo_plane_off;     // MODE 3: plane offset of the "lo" split of the A tensor ([hi planes][lo planes])
   int n_fast;           // tile order: N tiles of one M tile are consecutive (1x1 convs with several N tiles, see tc_conv_create)
   int tiles_n;
   int rows_a_bytes;     // ROWS mode: bytes of one A box ((BH+2) x BW x 128)
@@ -137,6 +140,18 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// kind::tf32 instruction descriptor: D=f32, A=B=tf32 (32-bit containers, 10-bit mantissa), both K-major, M x N; K = 8.
+__device__ __forceinline__ uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -385,21 +400,29 @@ constexpr int PATCH_STRIDE = 24 * 1024;                // per-buffer stride (102
 // barrier round covers 12 MMAs.
 constexpr int ROWS_A_SLOT = 20 * 1024;  // (8+2) rows x 16 px x 128 B (or 18 x 8 px for narrow images)
 
+// MODE 3 "fp32x3" (the fp32-accurate tensor-core mode, SURVEY 7 "Parity vs precision"): operands are fp32 tensors that were
+// split into hi = rn_tf32(x) and lo = rn_tf32(x - hi) (|x - hi - lo| <= 2^-22 |x|); a K chunk is 32 fp32 channels = the same
+// 128-byte swizzled row as 64 bf16 channels; per chunk the MMA warp issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo as three
+// groups of four tcgen05.mma.kind::tf32 (K=8) into the SAME fp32 TMEM accumulator (the dropped lo*lo term is 2^-22 relative).
+// The epilogue keeps everything in fp32 (IEEE SiLU, fp32 residual, fp32 NHWC / NCHW stores).
 template <int BN, int MODE>
 struct TcCfgP {
   static constexpr bool PATCH = MODE == 1;
   static constexpr bool ROWS = MODE == 2;
+  static constexpr bool TF3 = MODE == 3;
   static constexpr int B_STAGE_BYTES = BN * 128;
   // non-PATCH: G consecutive k-iterations (64-channel chunks) share one full/empty barrier round, which amortises the
   // mbarrier wait + tcgen05.commit of the single MMA-issuing thread over 4*G MMAs (matters for narrow N tiles)
   static constexpr int G = 1;  // measured: G=2 trades issue overhead for coarser prefetch granularity; no net gain
-  static constexpr int STAGES = ROWS ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
-                                     : (PATCH ? (BN == 256 ? 4 : (BN == 128 ? 8 : 12)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
-  static constexpr int BSUB = ROWS ? 3 : 1;  // weight tiles per stage
+  static constexpr int STAGES = TF3 ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
+                                : ROWS ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
+                                       : (PATCH ? (BN == 256 ? 4 : (BN == 128 ? 8 : 12)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+  static constexpr int BSUB = ROWS ? 3 : (TF3 ? 2 : 1);  // weight tiles per stage
   static constexpr int STAGE_BYTES = PATCH ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;  // per k-iteration (modes 0/1)
-  static constexpr int A_BYTES = ROWS ? STAGES * ROWS_A_SLOT : (PATCH ? 2 * PATCH_STRIDE : STAGES * G * A_STAGE_BYTES);
+  static constexpr int A_BYTES = TF3 ? STAGES * 2 * A_STAGE_BYTES
+                                     : (ROWS ? STAGES * ROWS_A_SLOT : (PATCH ? 2 * PATCH_STRIDE : STAGES * G * A_STAGE_BYTES));
   static constexpr int EPI_FLOATS = 3 * BN;
-  static constexpr int STG_BYTES = 8 * 2048;  // per epilogue warp: one 32 rows x 64 B staging tile for TMA stores
+  static constexpr int STG_BYTES = TF3 ? 0 : 8 * 2048;  // per epilogue warp: one 32 rows x 64 B staging tile for TMA stores
   static constexpr int SMEM_BYTES = 1024 + A_BYTES + STAGES * G * BSUB * B_STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 512;
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
@@ -469,6 +492,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   using Cfg = TcCfgP<BN, MODE>;
   constexpr bool PATCH = Cfg::PATCH;
   constexpr bool ROWS = Cfg::ROWS;
+  constexpr bool TF3 = Cfg::TF3;
   constexpr int STAGES = Cfg::STAGES;
   pdl_trigger();  // the next kernel may be scheduled; this one's prologue below touches no global memory
   extern __shared__ uint8_t smem_raw[];
@@ -528,7 +552,25 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       long long w_prod = 0, t_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(P, tile, tiles_m, BN);
-        if constexpr (ROWS) {
+        if constexpr (TF3) {
+          for (int ki = 0; ki < KI; ++ki, ++it) {
+            const int s = it % STAGES;
+            if (it >= STAGES) DBG_WAIT(w_prod, &empty_bar[s], ((it / STAGES) - 1) & 1);
+            if (elect_one()) {
+              const int tap = ki / P.kchunks, kc = ki - tap * P.kchunks;
+              const int dh = P.taps[tap].dh + (P.nphases == 4 ? t.py : 0);
+              const int dw = P.taps[tap].dw + (P.nphases == 4 ? t.px : 0);
+              const int wt = (t.phase * P.ntaps + tap) * 2;
+              mbar_expect_tx(&full_bar[s], 2 * A_STAGE_BYTES + 2 * Cfg::B_STAGE_BYTES);
+              tma_load_5d(smem_a + (s * 2 + 0) * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 32, t.w0 + dw, t.h0 + dh, t.b, P.taps[tap].plane);
+              tma_load_5d(smem_a + (s * 2 + 1) * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 32, t.w0 + dw, t.h0 + dh, t.b,
+                          P.taps[tap].plane + P.lo_plane_off);
+              tma_load_3d(smem_b + (s * 2 + 0) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 32, t.n0, wt);
+              tma_load_3d(smem_b + (s * 2 + 1) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 32, t.n0, wt + 1);
+            }
+            __syncwarp();
+          }
+        } else if constexpr (ROWS) {
           for (int kc = 0; kc < P.kchunks; ++kc) {
             for (int dwi = 0; dwi < 3; ++dwi, ++it) {
               const int s = it % STAGES;
@@ -592,7 +634,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp loops; one elected lane issues) =================
     {
-      const uint32_t idesc = make_idesc_bf16(128, BN);
+      const uint32_t idesc = TF3 ? make_idesc_tf32(128, BN) : make_idesc_bf16(128, BN);
       int it = 0, lt = 0, pc = 0;
       long long w_full = 0, w_tempty = 0, t_start = clock64();
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
@@ -600,7 +642,29 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
         if (lt >= 2) DBG_WAIT(w_tempty, &tempty_bar[acc], ((lt >> 1) - 1) & 1);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        if constexpr (ROWS) {
+        if constexpr (TF3) {
+          for (int ki = 0; ki < KI; ++ki, ++it) {
+            const int s = it % STAGES;
+            DBG_WAIT(w_full, &full_bar[s], (it / STAGES) & 1);
+            tc_fence_after();
+            if (elect_one()) {
+              const uint64_t a_hi = make_sw128_desc(smem_u32(smem_a + (s * 2 + 0) * A_STAGE_BYTES));
+              const uint64_t a_lo = make_sw128_desc(smem_u32(smem_a + (s * 2 + 1) * A_STAGE_BYTES));
+              const uint64_t b_hi = make_sw128_desc(smem_u32(smem_b + (s * 2 + 0) * Cfg::B_STAGE_BYTES));
+              const uint64_t b_lo = make_sw128_desc(smem_u32(smem_b + (s * 2 + 1) * Cfg::B_STAGE_BYTES));
+              // the two small cross terms first, the dominant hi*hi product last
+#pragma unroll
+              for (int k = 0; k < 4; ++k)  // 4 x (K=8 tf32) per 32-channel chunk: +32 B inside the swizzle atom
+                umma_tf32(tmem_d, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (ki > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, 1u);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, 1u);
+              umma_commit(&empty_bar[s]);
+            }
+            __syncwarp();
+          }
+        } else if constexpr (ROWS) {
           const int nst = 3 * P.kchunks;
           for (int si = 0; si < nst; ++si, ++it) {
             const int s = it % STAGES;
@@ -716,6 +780,45 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       const bf16* rrow = P.res ? P.res + opix * P.res_pitch + t.n0 : nullptr;
 
       auto process = [&](uint32_t* v, const int c0) {
+        if constexpr (TF3) {  // fp32 in, fp32 out: IEEE arithmetic, no fast-math approximations
+          if (affine) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), s_epi[c0 + j], s_epi[BN + c0 + j]));
+          }
+          if (P.silu) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = __uint_as_float(v[j]);
+              v[j] = __float_as_uint(x / (1.0f + expf(-x)));
+            }
+          }
+          if (P.out_nchw) {
+            if (pvalid && hh < P.cropH && ww < P.cropW) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int n = t.n0 + c0 + j;
+                if (n < P.Cout) P.out_nchw[(((long long)t.b * P.Cout + n) * P.cropH + hh) * P.cropW + ww] = __uint_as_float(v[j]);
+              }
+            }
+            return;
+          }
+          if (!pvalid) return;
+          float* of = P.out_f32 + opix * P.out_pitch + t.n0 + c0;
+          const float* rf = P.res_f32 ? P.res_f32 + opix * P.res_pitch + t.n0 + c0 : nullptr;
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            if (t.n0 + c0 + g * 4 < P.Cout) {
+              float4 o = make_float4(__uint_as_float(v[g * 4]), __uint_as_float(v[g * 4 + 1]), __uint_as_float(v[g * 4 + 2]),
+                                     __uint_as_float(v[g * 4 + 3]));
+              if (rf) {
+                const float4 r = *reinterpret_cast<const float4*>(rf + g * 4);
+                o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+              }
+              *reinterpret_cast<float4*>(of + g * 4) = o;
+            }
+          }
+          return;
+        }
         if (P.qsm && t.n0 + c0 < 128) {  // one chunk == one attention head of this pixel's q (module_util.py:168,171)
           float mx = __uint_as_float(v[0]);
 #pragma unroll
@@ -878,6 +981,9 @@ bool tc_init(std::string* err) {
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 2>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 1>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 3>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 3>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 3>::SMEM_BYTES);
   {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);
@@ -1047,6 +1153,95 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   return d;
 }
 
+// fp32x3 mode: `in_split` is the conv input split by launch_split_tf32: [2 (hi, lo)][planes][B][Hin][Win][Cin] fp32 (dense,
+// pixel pitch Cin); `wsplit` is [phase*ntaps][2 (hi, lo)][Cout_w][Cin] fp32 (pack_tc3_* kernels); fp32 NHWC output view.
+TcConvDesc* tc_conv_create_f32x3(const float* in_split, int B, int Hin, int Win, int Cin, int planes, const float* wsplit, int Cout,
+                                 int ntaps, const TcTap* taps, int nphases, const Epilogue& ep, float* out, int out_pitch, int Hout,
+                                 int Wout, std::string* err) {
+  auto bad = [&](const char* m) -> TcConvDesc* {
+    if (err) *err = m;
+    return nullptr;
+  };
+  if (!g_encode) return bad("tc_init not called");
+  if (!g_persist) return bad("fp32x3 needs the persistent kernel");
+  if (ntaps < 1 || ntaps > 16) return bad("ntaps out of range");
+  if (planes < 1) return bad("fp32x3: planes must be >= 1");
+  const bool nchw_out = (out == nullptr);
+  const int Cout_w = (Cout + 7) / 8 * 8;
+  if (Cin % 4) return bad("fp32x3: input channels must be a multiple of 4");
+  if (!nchw_out && (Cout % 4 || out_pitch % 4)) return bad("fp32x3: output channels / pitch must be multiples of 4");
+  if (((uintptr_t)in_split & 15) || ((uintptr_t)wsplit & 15) || ((uintptr_t)out & 15)) return bad("operands must be 16-byte aligned");
+  if (ep.res && (((uintptr_t)ep.res & 15) || ep.res_pitch % 4)) return bad("residual must be 16-byte aligned");
+  TcConvDesc* d = new TcConvDesc();
+  TcParams& P = d->P;
+  memset(&P, 0, sizeof P);
+  P.B = B; P.H = Hin; P.W = Win; P.Cin = Cin; P.Cout = Cout;
+  P.ntaps = ntaps; P.kchunks = (Cin + 31) / 32;
+  P.nphases = nphases;
+  P.Hout = Hout; P.Wout = Wout; P.os = nphases == 4 ? 2 : 1;
+  P.out = nullptr; P.out_f32 = out; P.out_pitch = out_pitch;
+  P.res = nullptr; P.res_f32 = (const float*)ep.res; P.res_pitch = ep.res_pitch;
+  P.bias = ep.bias; P.mult_vec = ep.mult_vec; P.ss = ep.ss; P.t_ptr = ep.t_ptr; P.ss_S = ep.ss_S; P.ss_off = ep.ss_off;
+  P.ss_img_stride = ep.ss_img_stride; P.silu = ep.silu;
+  P.lo_plane_off = planes;
+  for (int i = 0; i < ntaps; ++i) P.taps[i] = taps[i];
+  int BN = Cout > 64 ? 128 : (Cout > 32 ? 64 : 32);
+  d->patch = false;
+  d->mode = 3;
+  long long best = -1;
+  for (int bw = 128; bw >= 8; bw >>= 1) {
+    int bh = 128 / bw;
+    long long cost = (long long)((Win + bw - 1) / bw) * bw * ((Hin + bh - 1) / bh) * bh;
+    if (best < 0 || cost < best) { best = cost; P.BW = bw; P.BH = bh; }
+  }
+  P.logBW = 0;
+  while ((1 << P.logBW) < P.BW) P.logBW++;
+  P.tilesW = (Win + P.BW - 1) / P.BW;
+  P.tilesH = (Hin + P.BH - 1) / P.BH;
+  {
+    const int tm = P.tilesW * P.tilesH * B * nphases;
+    while (BN > 32 && Cout % (BN / 2) == 0 && (long long)tm * ((Cout + BN - 1) / BN) < 74) BN >>= 1;
+  }
+  d->BN = BN;
+  d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
+  d->tiles_m = P.tilesW * P.tilesH * B * nphases;
+  d->num_tiles = d->tiles_m * ((Cout + BN - 1) / BN);
+  P.tiles_n = (Cout + BN - 1) / BN;
+  P.n_fast = 0;
+  {
+    cuuint64_t dims[5] = {(cuuint64_t)Cin, (cuuint64_t)Win, (cuuint64_t)Hin, (cuuint64_t)B, (cuuint64_t)(2 * planes)};
+    cuuint64_t strides[4] = {(cuuint64_t)Cin * 4, (cuuint64_t)Win * Cin * 4, (cuuint64_t)Hin * Win * Cin * 4,
+                             (cuuint64_t)B * Hin * Win * Cin * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1, 1};
+    cuuint32_t es[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(&d->map_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in_split, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete d;
+      if (err) { char b[96]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(A fp32) failed: %d", (int)r); *err = b; }
+      return nullptr;
+    }
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout_w, (cuuint64_t)(nphases * ntaps * 2)};
+    cuuint64_t strides[2] = {(cuuint64_t)Cin * 4, (cuuint64_t)Cout_w * Cin * 4};
+    cuuint32_t box[3] = {32, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = g_encode(&d->map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)wsplit, dims, strides, box, es,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      delete d;
+      if (err) { char b[96]; snprintf(b, sizeof b, "cuTensorMapEncodeTiled(B fp32) failed: %d", (int)r); *err = b; }
+      return nullptr;
+    }
+  }
+  memset(&d->map_o, 0, sizeof d->map_o);
+  P.tma_store = 0;
+  return d;
+}
+
 void tc_conv_destroy(TcConvDesc* d) { delete d; }
 
 bool tc_fused_attention_available() { return g_persist && g_tma_store; }
@@ -1076,7 +1271,13 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
     d->P.dbg = dbg ? dbg_dev : nullptr;
 #define TC_LAUNCH(BNV, PV) \
   pdl_launch(conv_tc_persist_kernel<BNV, PV>, g, 320, TcCfgP<BNV, PV>::SMEM_BYTES, st, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles)
-    if (d->mode == 2) {
+    if (d->mode == 3) {
+      switch (d->BN) {
+        case 32: TC_LAUNCH(32, 3); break;
+        case 64: TC_LAUNCH(64, 3); break;
+        default: TC_LAUNCH(128, 3); break;
+      }
+    } else if (d->mode == 2) {
       switch (d->BN) {
         case 32: TC_LAUNCH(32, 2); break;
         case 64: TC_LAUNCH(64, 2); break;

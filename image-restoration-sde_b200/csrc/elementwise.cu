@@ -388,6 +388,36 @@ void launch_space_to_depth(const T* in, int in_pitch, T* out, int B, int H, int 
   long long total = (long long)B * H * W * (C / vec);
   pdl_launch(s2d_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, in, in_pitch, out, B, H, W, C);
 }
+// =============================================================================================
+// fp32x3 operand split: hi = rn_tf32(x) (10-bit mantissa, low 13 bits zero), lo = rn_tf32(x - hi).  x - hi is exact in
+// fp32, so x = hi + lo + r with |r| <= 2^-22 |x|: three tf32 MMAs (hi*hi + lo*hi + hi*lo) reproduce the fp32 product to
+// 2^-21 relative.  Both parts carry explicit zero low bits, so the result does not depend on how the tensor core
+// treats the 13 bits kind::tf32 ignores.
+// =============================================================================================
+__device__ __forceinline__ float rn_tf32(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void split_tf32_kernel(const float* __restrict__ in, int pitch, float* __restrict__ out, long long npix, int C) {
+  PDL_ENTRY();
+  const int cg = C >> 2;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= npix * cg) return;
+  const long long pix = idx / cg;
+  const int g = (int)(idx - pix * cg);
+  const float4 v = *reinterpret_cast<const float4*>(in + pix * pitch + g * 4);
+  float4 h, l;
+  h.x = rn_tf32(v.x); h.y = rn_tf32(v.y); h.z = rn_tf32(v.z); h.w = rn_tf32(v.w);
+  l.x = rn_tf32(v.x - h.x); l.y = rn_tf32(v.y - h.y); l.z = rn_tf32(v.z - h.z); l.w = rn_tf32(v.w - h.w);
+  *reinterpret_cast<float4*>(out + pix * C + g * 4) = h;
+  *reinterpret_cast<float4*>(out + (npix + pix) * C + g * 4) = l;
+}
+void launch_split_tf32(const float* in, int in_pitch, float* out, long long npix, int C, cudaStream_t st) {
+  long long total = npix * (C >> 2);
+  pdl_launch(split_tf32_kernel, (unsigned)((total + 255) / 256), 256, 0, st, in, in_pitch, out, npix, C);
+}
+
 template void launch_space_to_depth<bf16>(const bf16*, int, bf16*, int, int, int, int, cudaStream_t);
 template void launch_space_to_depth<float>(const float*, int, float*, int, int, int, int, cudaStream_t);
 

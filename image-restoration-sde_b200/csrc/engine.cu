@@ -105,6 +105,8 @@ struct irsde_ctx {
   bool finalized = false;
   std::map<std::string, float*> w_simt;  // [KH*KW][Cin][Cout] fp32
   std::map<std::string, bf16*> w_tc;     // [phase][tap][Cout][Cin] bf16
+  std::map<std::string, float*> w_tc3;   // fp32x3: [phase][tap][2 (hi,lo)][Cout_pad][Cin] fp32 (tf32-rounded parts)
+  bool use_tc3 = false;                  // fp32x3 mode: fp32 storage, convs through 3 x tcgen05.mma.kind::tf32
   std::map<std::string, int> ss_off;
   float *wall = nullptr, *ball = nullptr;
   int S = 0;
@@ -230,6 +232,51 @@ __global__ void pack_tc_padded_kernel(const float* __restrict__ w, bf16* __restr
   int tap = idx / ((long long)Cout_pad * Cin);
   int r = tap / KW, s = tap % KW;
   o[idx] = __float2bfloat16_rn(co < Cout ? w[(((long long)co * Cin + c) * KH + r) * KW + s] : 0.f);
+}
+
+// fp32x3 weights: [tap][2 (hi, lo)][Cout_pad][Cin] fp32, hi = rn_tf32(w), lo = rn_tf32(w - hi) (zero rows for co >= Cout)
+__device__ __forceinline__ float rn_tf32_w(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+__global__ void pack_tc3_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cout_pad, int Cin, int KH, int KW) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)Cout_pad * Cin * KH * KW;
+  if (idx >= total) return;
+  int c = idx % Cin;
+  int co = (idx / Cin) % Cout_pad;
+  int tap = idx / ((long long)Cout_pad * Cin);
+  int r = tap / KW, s = tap % KW;
+  float v = co < Cout ? w[(((long long)co * Cin + c) * KH + r) * KW + s] : 0.f;
+  float hi = rn_tf32_w(v);
+  long long base = ((long long)tap * 2 * Cout_pad + co) * Cin + c;
+  o[base] = hi;
+  o[base + (long long)Cout_pad * Cin] = rn_tf32_w(v - hi);
+}
+// nearest-x2 + 3x3 as four 2x2 phase convolutions (see pack_tc_up_kernel): [phase][tap][2][Cout_pad][Cin]
+__global__ void pack_tc3_up_kernel(const float* __restrict__ w, float* __restrict__ o, int Cout, int Cout_pad, int Cin) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)16 * Cout_pad * Cin;
+  if (idx >= total) return;
+  int c = idx % Cin;
+  int co = (idx / Cin) % Cout_pad;
+  int tap = (idx / ((long long)Cout_pad * Cin)) % 4;
+  int phase = idx / ((long long)4 * Cout_pad * Cin);
+  int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+  int r0, r1, s0, s1;
+  if (py == 0) { if (a == 0) { r0 = 0; r1 = 0; } else { r0 = 1; r1 = 2; } }
+  else         { if (a == 0) { r0 = 0; r1 = 1; } else { r0 = 2; r1 = 2; } }
+  if (px == 0) { if (b == 0) { s0 = 0; s1 = 0; } else { s0 = 1; s1 = 2; } }
+  else         { if (b == 0) { s0 = 0; s1 = 1; } else { s0 = 2; s1 = 2; } }
+  float acc = 0.f;
+  if (co < Cout)
+    for (int r = r0; r <= r1; ++r)
+      for (int q = s0; q <= s1; ++q) acc += w[(((long long)co * Cin + c) * 3 + r) * 3 + q];
+  float hi = rn_tf32_w(acc);
+  long long base = (((long long)(phase * 4 + tap) * 2) * Cout_pad + co) * Cin + c;
+  o[base] = hi;
+  o[base + (long long)Cout_pad * Cin] = rn_tf32_w(acc - hi);
 }
 
 // ---- architecture description --------------------------------------------------------------------
@@ -589,6 +636,70 @@ struct Builder {
         TcConvDesc* d = tc_conv_create(a_ptr, a_pitch, plan->B, Ha, Wa, in.C, planes, wt, Cout, ntaps, taps, nph, ep, out.p,
                                        out.pitch, g.Hout, g.Wout, &terr, tc_flags);
         if (!d) { ok = false; err = "tc_conv_create(" + wname + "): " + terr; return; }
+        plan->tc_descs.push_back(d);
+        int cH = nchw_H ? nchw_H : plan->H, cW = nchw_W ? nchw_W : plan->W;
+        plan->ops.push_back(OpRec{CAT_TC, tc_flops, [=](Plan* p, cudaStream_t st) {
+          if (use_ss) tc_conv_set_runtime(d, p->cur.ss, p->cur.t_ptr, p->cur.ss_img_stride);
+          if (nchw) tc_conv_set_out_nchw(d, p->cur.out, cH, cW);
+          tc_conv_launch(d, st);
+          c->launches++;
+        }});
+        return;
+      }
+    }
+    if constexpr (std::is_same<T, float>::value) {
+      bool shape_ok = (K == 3 && stride == 1 && pad == 1) || (K == 1 && stride == 1 && pad == 0 && up == 1) ||
+                      (K == 4 && stride == 2 && pad == 1 && up == 1 && Hin % 2 == 0 && Win % 2 == 0) ||
+                      (K == 2 && stride == 2 && pad == 0 && up == 1 && Hin % 2 == 0 && Win % 2 == 0);
+      if (ctx->use_tc3 && shape_ok && !tc_flags && !w_override && in.C % 4 == 0 && in.pitch % 4 == 0 &&
+          (((uintptr_t)in.p) & 15) == 0 && (nchw ? (K == 3 && up == 1) : (Cout % 4 == 0 && out.pitch % 4 == 0))) {
+        const float* wt = ctx->w_tc3[wname];
+        if (!wt) { ok = false; err = "unpacked fp32x3 weight " + wname; return; }
+        TcTap taps[16];
+        int ntaps = 0, nph = 1, planes = 1, Ha = Hin, Wa = Win;
+        const float* a_src = in.p;
+        int a_pitch = in.pitch;
+        if (K == 3 && up == 1) {
+          for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) taps[ntaps++] = TcTap{r - 1, q - 1, 0};
+        } else if (K == 3 && up == 2) {
+          nph = 4;
+          for (int a = 0; a < 2; ++a) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{a - 1, q - 1, 0};
+        } else if (K == 1) {
+          taps[ntaps++] = TcTap{0, 0, 0};
+        } else {
+          static const int PY[4] = {1, 0, 1, 0}, DH[4] = {-1, 0, 0, 1};
+          if (K == 4) {
+            for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) taps[ntaps++] = TcTap{DH[r], DH[q], PY[r] * 2 + PY[q]};
+          } else {
+            for (int r = 0; r < 2; ++r) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{0, 0, r * 2 + q};
+          }
+          planes = 4; Ha = Hin / 2; Wa = Win / 2;
+          float* s2d = tmp((long long)plan->B * Hin * Win * in.C);
+          int Bc = plan->B, Cc = in.C;
+          plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
+            launch_space_to_depth<float>(in.p, in.pitch, s2d, Bc, Hin, Win, Cc, st);
+            c->launches++;
+          }});
+          a_src = s2d; a_pitch = in.C;
+          release(s2d);
+        }
+        // operand split (hi, lo) of the conv input: [2][planes][B][Ha][Wa][C]
+        const long long npix_a = (long long)planes * plan->B * Ha * Wa;
+        float* split = tmp(2 * npix_a * in.C);
+        {
+          int Cc = in.C;
+          plan->ops.push_back(OpRec{CAT_MISC, 0.0, [=](Plan*, cudaStream_t st) {
+            launch_split_tf32(a_src, a_pitch, split, npix_a, Cc, st);
+            c->launches++;
+          }});
+          plan->ops.back().label = wname + " tf32 hi/lo split of the input";
+          plan->ops.back().bytes = 3.0 * npix_a * in.C * 4.0;
+        }
+        std::string terr;
+        TcConvDesc* d = tc_conv_create_f32x3(split, plan->B, Ha, Wa, in.C, planes, wt, Cout, ntaps, taps, nph, ep, out.p, out.pitch,
+                                             g.Hout, g.Wout, &terr);
+        release(split);
+        if (!d) { ok = false; err = "tc_conv_create_f32x3(" + wname + "): " + terr; return; }
         plan->tc_descs.push_back(d);
         int cH = nchw_H ? nchw_H : plan->H, cW = nchw_W ? nchw_W : plan->W;
         plan->ops.push_back(OpRec{CAT_TC, tc_flops, [=](Plan* p, cudaStream_t st) {
@@ -1152,7 +1263,7 @@ int build_plan(irsde_ctx* ctx, int B, int H, int W, Plan** out) {
   p->B = B; p->H = H; p->W = W;
   std::string err;
   bool ok;
-  if (ctx->cfg.precision == IRSDE_PREC_FP32) {
+  if (ctx->cfg.precision != IRSDE_PREC_BF16) {
     Builder<float> b{ctx, p};
     if (ctx->lat.on) b.build_latent(); else if (ctx->naf.on) b.build_naf(); else b.build();
     ok = b.ok; err = b.err;
@@ -1311,7 +1422,7 @@ int irsde_create(const irsde_config* cfg, irsde_ctx** out) {
     return fail(nullptr, IRSDE_ERR_INVALID, "bad network configuration");
   if (cfg->variant != IRSDE_NET_CONDITIONAL && cfg->variant != IRSDE_NET_DENOISING)
     return fail(nullptr, IRSDE_ERR_INVALID, "bad variant");
-  if (cfg->precision != IRSDE_PREC_FP32 && cfg->precision != IRSDE_PREC_BF16)
+  if (cfg->precision != IRSDE_PREC_FP32 && cfg->precision != IRSDE_PREC_BF16 && cfg->precision != IRSDE_PREC_FP32X3)
     return fail(nullptr, IRSDE_ERR_INVALID, "bad precision");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1325,11 +1436,12 @@ int irsde_create(const irsde_config* cfg, irsde_ctx** out) {
   if (cudaSetDevice(cfg->device) != cudaSuccess) { delete c; return fail(nullptr, IRSDE_ERR_CUDA, "cudaSetDevice failed"); }
   std::string terr;
   c->tc_ok = tc_init(&terr);
-  if (cfg->precision == IRSDE_PREC_BF16 && !c->tc_ok) {
+  if (cfg->precision != IRSDE_PREC_FP32 && !c->tc_ok) {
     delete c;
     return fail(nullptr, IRSDE_ERR_CUDA, "tensor-core engine init failed: " + terr);
   }
   c->use_tc = cfg->precision == IRSDE_PREC_BF16 && !(cfg->flags & IRSDE_FLAG_FORCE_SIMT);
+  c->use_tc3 = cfg->precision == IRSDE_PREC_FP32X3 && !(cfg->flags & IRSDE_FLAG_FORCE_SIMT);
   for (int i = 0; i <= cfg->depth; ++i) c->udim.push_back(cfg->nf * (1 << i));
   *out = c;
   return IRSDE_OK;
@@ -1594,6 +1706,19 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
     if (!ws) ws = (float*)dev_alloc(ctx, (size_t)n * 4, &ctx->allocs);
     if (!ws) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
     pack_simt_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, ws, Cout, Cin, KH, KW);
+    if (ctx->cfg.precision == IRSDE_PREC_FP32X3 && !(KH == 7)) {
+      bool is_up = s.name.find(".3.1.weight") != std::string::npos && KH == 3;
+      int Cout_pad = (Cout + 7) / 8 * 8;
+      long long nt = (long long)(is_up ? 16 : KH * KW) * 2 * Cout_pad * Cin;
+      float*& wt = ctx->w_tc3[s.name];
+      if (!wt) wt = (float*)dev_alloc(ctx, (size_t)nt * 4, &ctx->allocs);
+      if (!wt) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+      long long nthreads = nt / 2;
+      if (is_up)
+        pack_tc3_up_kernel<<<(unsigned)((nthreads + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cout_pad, Cin);
+      else
+        pack_tc3_kernel<<<(unsigned)((nthreads + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cout_pad, Cin, KH, KW);
+    }
     if (ctx->cfg.precision == IRSDE_PREC_BF16) {
       bool is_up = s.name.find(".3.1.weight") != std::string::npos;
       bool is_stem = s.name == "init_conv.weight" && KH == 7;
@@ -1907,7 +2032,7 @@ int irsde_trace_forward(irsde_ctx* ctx, const float* x, const float* mu, const f
   p->cur.x = x; p->cur.mu = mu; p->cur.out = p->eps_buf;
   p->cur.ss = p->fwd_table; p->cur.t_ptr = p->d_zero; p->cur.ss_img_stride = (n_times > 1) ? 1 : 0;
   for (int i = 0; i <= op; ++i) p->ops[i].fn(p, st);
-  if (ctx->cfg.precision == IRSDE_PREC_FP32)
+  if (ctx->cfg.precision != IRSDE_PREC_BF16)
     launch_nhwc_to_nchw<float>((const float*)r.out_p, r.out_pitch, dump, B, r.out_C, r.out_H, r.out_W, st);
   else
     launch_nhwc_to_nchw<bf16>((const bf16*)r.out_p, r.out_pitch, dump, B, r.out_C, r.out_H, r.out_W, st);
@@ -1929,8 +2054,8 @@ int irsde_conv2d_ex(irsde_ctx* ctx, int32_t engine, const float* x, const float*
                     int32_t pad, int32_t upsample, int32_t silu, int32_t flags, void* stream) {
   if (!ctx || !x || !w || !y) return fail(ctx, IRSDE_ERR_INVALID, "null argument");
   const bool f_qsm = (flags & IRSDE_CONV_QSOFTMAX) != 0, f_wimg = (flags & IRSDE_CONV_W_PER_IMAGE) != 0;
-  if ((f_qsm || f_wimg || residual) && engine != 1)
-    return fail(ctx, IRSDE_ERR_UNSUPPORTED, "flags / residual are epilogues of the tensor-core engine");
+  if ((f_qsm || f_wimg) && engine != 1) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "q-softmax / per-image weights are bf16 tensor-core epilogues");
+  if (residual && engine == 0) return fail(ctx, IRSDE_ERR_UNSUPPORTED, "residual is an epilogue of the tensor-core engines");
   if ((f_qsm || f_wimg) && !(KH == 1 && KW == 1 && stride == 1 && pad == 0 && !upsample && Cout % 8 == 0))
     return fail(ctx, IRSDE_ERR_INVALID, "q-softmax / per-image weights need a 1x1 conv with Cout % 8 == 0");
   if (f_qsm && Cout < 128) return fail(ctx, IRSDE_ERR_INVALID, "q-softmax needs Cout >= 128 (4 heads x 32)");
@@ -2011,6 +2136,69 @@ int irsde_conv2d_ex(irsde_ctx* ctx, int32_t engine, const float* x, const float*
       cudaError_t e = cudaStreamSynchronize(st);
       if (e == cudaSuccess) e = cudaGetLastError();
       if (e != cudaSuccess) rc = fail(ctx, IRSDE_ERR_CUDA, std::string("tensor-core conv2d failed: ") + cudaGetErrorString(e));
+    }
+    if (d) tc_conv_destroy(d);
+    for (void* q : tmp) cudaFree(q);
+    return rc;
+  }
+  if (engine == 2) {
+    // fp32x3 engine: fp32 NHWC, hi/lo split, 3 x tcgen05.mma.kind::tf32 (conv_tc.cu MODE 3)
+    std::string terr;
+    if (!tc_init(&terr)) return fail(ctx, IRSDE_ERR_CUDA, "tc_init: " + terr);
+    bool k3 = KH == 3 && KW == 3 && stride == 1 && pad == 1, k1 = KH == 1 && KW == 1 && stride == 1 && pad == 0 && up == 1,
+         k4 = KH == 4 && KW == 4 && stride == 2 && pad == 1 && up == 1 && H % 2 == 0 && W % 2 == 0;
+    bool nchw = Cout % 4 != 0;
+    if (!(k3 || k1 || k4) || Cin % 4 || (nchw && !(k3 && up == 1)) || residual && nchw)
+      return fail(ctx, IRSDE_ERR_UNSUPPORTED, "shape not supported by the fp32x3 engine");
+    int Ho = (H * up + 2 * pad - KH) / stride + 1, Wo = (W * up + 2 * pad - KW) / stride + 1;
+    int Cout_pad = (Cout + 7) / 8 * 8;
+    std::vector<void*> tmp;
+    long long nin = (long long)B * H * W * Cin, nout = (long long)B * Ho * Wo * Cout;
+    long long nwt = (long long)((k3 && up == 2) ? 16 : KH * KW) * 2 * Cout_pad * Cin;
+    float* xin = (float*)dev_alloc(ctx, nin * 4, &tmp);
+    float* xs2d = (float*)dev_alloc(ctx, nin * 4, &tmp);
+    float* xsp = (float*)dev_alloc(ctx, 2 * nin * 4, &tmp);
+    float* wp = (float*)dev_alloc(ctx, nwt * 4, &tmp);
+    float* yo = (float*)dev_alloc(ctx, (nout + 16) * 4, &tmp);
+    float* resb = residual ? (float*)dev_alloc(ctx, nout * 4, &tmp) : nullptr;
+    int rc = IRSDE_OK;
+    TcConvDesc* d = nullptr;
+    if (!xin || !xs2d || !xsp || !wp || !yo || (residual && !resb)) rc = fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
+    if (!rc) {
+      launch_nchw_to_nhwc<float>(x, xin, B, Cin, H, W, Cin, st);
+      if (resb) launch_nchw_to_nhwc<float>(residual, resb, B, Cout, Ho, Wo, Cout, st);
+      if (k3 && up == 2) pack_tc3_up_kernel<<<(unsigned)((nwt / 2 + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cout_pad, Cin);
+      else pack_tc3_kernel<<<(unsigned)((nwt / 2 + 255) / 256), 256, 0, st>>>(w, wp, Cout, Cout_pad, Cin, KH, KW);
+      TcTap taps[16];
+      int ntaps = 0, nph = 1, planes = 1, Ha = H, Wa = W;
+      const float* a_src = xin;
+      if (k3 && up == 1) { for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) taps[ntaps++] = TcTap{r - 1, q - 1, 0}; }
+      else if (k3) { nph = 4; for (int a = 0; a < 2; ++a) for (int q = 0; q < 2; ++q) taps[ntaps++] = TcTap{a - 1, q - 1, 0}; }
+      else if (k1) { taps[ntaps++] = TcTap{0, 0, 0}; }
+      else {
+        static const int PY[4] = {1, 0, 1, 0}, DH[4] = {-1, 0, 0, 1};
+        for (int r = 0; r < 4; ++r) for (int q = 0; q < 4; ++q) taps[ntaps++] = TcTap{DH[r], DH[q], PY[r] * 2 + PY[q]};
+        planes = 4; Ha = H / 2; Wa = W / 2;
+        launch_space_to_depth<float>(xin, Cin, xs2d, B, H, W, Cin, st);
+        a_src = xs2d;
+      }
+      launch_split_tf32(a_src, Cin, xsp, (long long)planes * B * Ha * Wa, Cin, st);
+      Epilogue ep;
+      memset(&ep, 0, sizeof ep);
+      ep.bias = bias;
+      ep.silu = silu;
+      if (resb) { ep.res = resb; ep.res_pitch = Cout; }
+      d = tc_conv_create_f32x3(xsp, B, Ha, Wa, Cin, planes, wp, Cout, ntaps, taps, nph, ep, nchw ? nullptr : yo, Cout, Ho, Wo, &terr);
+      if (!d) rc = fail(ctx, IRSDE_ERR_INVALID, "tc_conv_create_f32x3: " + terr);
+    }
+    if (!rc) {
+      if (nchw) tc_conv_set_out_nchw(d, y, Ho, Wo);
+      tc_conv_launch(d, st);
+      if (!nchw) launch_nhwc_to_nchw<float>(yo, Cout, y, B, Cout, Ho, Wo, st);
+      ctx->launches += 5;
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e == cudaSuccess) e = cudaGetLastError();
+      if (e != cudaSuccess) rc = fail(ctx, IRSDE_ERR_CUDA, std::string("fp32x3 conv2d failed: ") + cudaGetErrorString(e));
     }
     if (d) tc_conv_destroy(d);
     for (void* q : tmp) cudaFree(q);

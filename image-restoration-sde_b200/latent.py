@@ -108,8 +108,8 @@ class UNet(ConditionalUNet):
         self.in_ch, self.out_ch, self.ch, self.ch_mult, self.embed_dim = in_ch, out_ch, ch, list(ch_mult), embed_dim
         self.depth = len(ch_mult)
         self.precision = precision or os.environ.get("IRSDE_B200_PRECISION", "fp32")
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % (sorted(_lib.PRECISIONS),))
         self._force_simt = force_simt
         self._shapes = latent_unet_param_shapes(in_ch, out_ch, ch, ch_mult, embed_dim)
         for name, shp in self._shapes.items():
@@ -132,7 +132,7 @@ class UNet(ConditionalUNet):
             if self._ctx is not None:
                 self._ctx.close()
             self._ctx = _LatContext(self.in_ch, self.out_ch, self.ch, self.ch_mult, self.embed_dim,
-                                    _lib.PREC_FP32 if self.precision == "fp32" else _lib.PREC_BF16, idx,
+                                    _lib.PRECISIONS[self.precision], idx,
                                     force_simt=self._force_simt)
             self._ctx_dev = idx
             self._sig = None

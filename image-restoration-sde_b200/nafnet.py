@@ -97,8 +97,8 @@ class ConditionalNAFNet(ConditionalUNet):
         self.enc_blk_nums, self.dec_blk_nums = list(enc_blk_nums), list(dec_blk_nums)
         self.upscale, self.latent = upscale, latent
         self.precision = precision or os.environ.get("IRSDE_B200_PRECISION", "fp32")
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % (sorted(_lib.PRECISIONS),))
         self._force_simt = force_simt
         self._shapes = nafnet_param_shapes(img_channel, width, middle_blk_num, enc_blk_nums, dec_blk_nums)
         for name, shp in self._shapes.items():
@@ -125,7 +125,7 @@ class ConditionalNAFNet(ConditionalUNet):
             if self._ctx is not None:
                 self._ctx.close()
             self._ctx = _NafContext(self.img_channel, self.width, self.middle_blk_num, self.enc_blk_nums, self.dec_blk_nums,
-                                    self.latent, _lib.PREC_FP32 if self.precision == "fp32" else _lib.PREC_BF16, idx,
+                                    self.latent, _lib.PRECISIONS[self.precision], idx,
                                     force_simt=self._force_simt)
             self._ctx_dev = idx
             self._sig = None

@@ -100,8 +100,8 @@ class ConditionalUNet(nn.Module):
         self.ch_mult = ch_mult
         self.in_nc, self.out_nc, self.nf, self.depth, self.upscale = in_nc, out_nc, nf, depth, upscale
         self.precision = precision or os.environ.get("IRSDE_B200_PRECISION", "fp32")
-        if self.precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if self.precision not in _lib.PRECISIONS:
+            raise ValueError("precision must be one of %s" % (sorted(_lib.PRECISIONS),))
         self._force_simt = force_simt
         self._shapes = unet_param_shapes(in_nc, out_nc, nf, depth, self.variant, ch_mult)
         for name, shp in self._shapes.items():
@@ -140,7 +140,7 @@ class ConditionalUNet(nn.Module):
                 self._ctx.close()
             self._ctx = _lib.Context(self.in_nc, self.out_nc, self.nf, self.depth,
                                      _lib.NET_CONDITIONAL if self.variant == "conditional" else _lib.NET_DENOISING,
-                                     _lib.PREC_FP32 if self.precision == "fp32" else _lib.PREC_BF16, idx,
+                                     _lib.PRECISIONS[self.precision], idx,
                                      force_simt=self._force_simt, ch_mult=self.ch_mult)
             self._ctx_dev = idx
             self._sig = None

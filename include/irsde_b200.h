@@ -41,6 +41,10 @@ typedef enum {
 #define IRSDE_PREC_FP32 0 /* parity mode: fp32 storage + fp32 FMA everywhere                     */
 #define IRSDE_PREC_BF16 1 /* perf mode: bf16 activations/weights, tcgen05 MMA, fp32 accumulate,  */
                           /* fp32 sampler state                                                   */
+#define IRSDE_PREC_FP32X3 2 /* fp32-accurate tensor-core mode: fp32 storage; every conv is three   */
+                            /* tcgen05.mma.kind::tf32 passes over hi/lo split operands            */
+                            /* (hi*hi + lo*hi + hi*lo, fp32 accumulate in TMEM): meets the 1e-3    */
+                            /* bound of the fp32 mode on the tensor cores                          */
 
 /* sampler */
 #define IRSDE_MODE_SDE 0       /* IRSDE.reverse_sde        codes/utils/sde_utils.py:252-266 */
@@ -183,7 +187,7 @@ int64_t irsde_device_bytes(const irsde_ctx* ctx);
 
 /* ---- standalone operator entry points (unit-test / micro-benchmark surface) -------------- */
 /* Generic NHWC convolution through the engine selected by `engine` (0 = fp32 SIMT implicit
- * GEMM, 1 = tcgen05 bf16 tap-GEMM).  Input/weights/output are fp32 device buffers:
+ * GEMM, 1 = tcgen05 bf16 tap-GEMM, 2 = tcgen05 fp32x3 tap-GEMM: fp32 in/out, 3 x kind::tf32 MMA).  Input/weights/output are fp32 device buffers:
  * x [B,Cin,H,W], w [Cout,Cin,KH,KW] (nn.Conv2d layout, module_util.py:96,101,105), y
  * [B,Cout,Ho,Wo]; the call repacks to the engine's layout, runs, and unpacks. */
 int irsde_conv2d(irsde_ctx* ctx, int32_t engine, const float* x, const float* w, const float* bias, float* y,
