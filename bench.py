@@ -377,7 +377,7 @@ def run_b200(args):
         lq_cpu, xT_cpu = lq_cpu[lo:hi].contiguous(), xT_cpu[lo:hi].contiguous()
         lq, xT = lq_cpu.to(dev), xT_cpu.to(dev)
         rev = getattr(sde, "reverse_" + w["mode"])
-        ctxs = [net._ctx]
+        ctxs = [net.sync_weights(dev)]
 
         def chain_resident(Tn=-1):
             outs = []
@@ -427,8 +427,7 @@ def run_b200(args):
         lq_cpu, g = synth(B_glob, w["H"], w["W"], seed=1234)
         lq = lq_cpu.to(dev)
         pipe = irsde_b200.TiledRefusion(ae, sde, tile=w["tile"], mode=w["mode"], seed=7)
-        ae.sync_weights(dev)
-        ctxs = [net._ctx if net._ctx else net.sync_weights(dev), ae._ctx]
+        ctxs = [net.sync_weights(dev), ae.sync_weights(dev)]
 
         def chain_resident(Tn=-1):
             if Tn >= 0:   # instrumented pass: a few steps of the chain on this rank's first tile batch

@@ -24,7 +24,7 @@ SYMBOLS = ["irsde_create", "irsde_create_ch_mult", "irsde_create_nafnet", "irsde
            "irsde_finalize_weights", "irsde_set_schedule", "irsde_set_coeffs", "irsde_noise_fn", "irsde_step",
            "irsde_reverse", "irsde_noise_state", "irsde_noise_state_images", "irsde_set_image_base", "irsde_set_image_uids", "irsde_comm_unique_id", "irsde_comm_init", "irsde_broadcast_weights", "irsde_gather", "irsde_launch_count", "irsde_device_bytes", "irsde_conv2d", "irsde_profile_begin",
            "irsde_profile_end", "irsde_profile_end_bytes", "irsde_conv2d_ex", "irsde_plan_num_ops", "irsde_plan_op_info", "irsde_trace_forward",
-           "irsde_trim"]
+           "irsde_trim", "irsde_random_states"]
 
 
 class Config(ctypes.Structure):
@@ -100,6 +100,8 @@ def load():
     L.irsde_broadcast_weights.restype = ctypes.c_int
     L.irsde_gather.argtypes = [vp, vp, vp, ctypes.POINTER(i64), vp]
     L.irsde_gather.restype = ctypes.c_int
+    L.irsde_random_states.argtypes = [vp, vp, vp, vp, vp, vp, i32, i64, vp]
+    L.irsde_random_states.restype = ctypes.c_int
     L.irsde_trim.argtypes = [vp]
     L.irsde_trim.restype = ctypes.c_int
     L.irsde_profile_begin.argtypes = [vp]

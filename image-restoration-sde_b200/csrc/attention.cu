@@ -674,9 +674,183 @@ __global__ void __launch_bounds__(128) fullattn_kernel(const T* __restrict__ qkv
     for (int d = 0; d < 32; ++d) orow[d] = from_f<T>(acc[d] / l);
   }
 }
+// ---------------------------------------------------------------------------------------------
+// bf16 perf-mode version: flash attention on the tensor cores (module_util.py:192-204: q*32^-.5, sim = q^T k,
+// softmax_j, out = attn v).  One CTA = 64 queries of one (image, head); warp w owns query rows 16w..16w+15.
+// Per 64-key block: S = Q K^T by mma.sync m16n8k16 (bf16 x bf16 -> fp32; K rows are the natural col-major B operand),
+// online softmax on the accumulator fragments (row max / sum across the 4 lanes of a quad by shuffles), P re-packed in
+// registers as the bf16 A operand of the second product (the FlashAttention-2 register reuse, no smem round trip),
+// O += P V with V fragments from ldmatrix.trans.  K and V tiles stream through a double-buffered cp.async ring.
+// Arithmetic intensity note: with d = 32 every score costs 64 tensor MACs but one ex2 on the 16/clk/SM
+// MUFU pipe, so this kernel is MUFU-bound by ~8x - the tensor pipe cannot exceed ~12 % here whatever the MMA flavour
+// (tcgen05 would not change that; it is why this stays on mma.sync, whose operands come straight from registers).
+// ---------------------------------------------------------------------------------------------
+static const int FA_Q = 64, FA_K = 64, FA_P = 40;  // queries / keys per block; smem row pitch (32 + 8 pad, bf16)
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+               : "r"(addr));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__global__ void __launch_bounds__(128) fullattn_mma_kernel(const bf16* __restrict__ qkv, int pitch, bf16* __restrict__ hidden,
+                                                           int hid_pitch, int N) {
+  PDL_ENTRY();
+  __shared__ __align__(16) bf16 Qs[FA_Q * FA_P];
+  __shared__ __align__(16) bf16 Ks[2][FA_K * FA_P];
+  __shared__ __align__(16) bf16 Vs[2][FA_K * FA_P];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int bh = blockIdx.y, b = bh >> 2, h = bh & 3;
+  const int q0 = blockIdx.x * FA_Q;
+  const bf16* base = qkv + (long long)b * N * pitch + h * 32;
+
+  auto load_kv = [&](int j0, int buf) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = tid + i * 128;  // 512 16-byte vectors: 64 keys x (4 of K + 4 of V)
+      const int key = v >> 3, part = v & 7, isv = part >> 2, j = part & 3;
+      bf16* d = (isv ? Vs[buf] : Ks[buf]) + key * FA_P + j * 8;
+      if (j0 + key < N) {
+        const bf16* src = base + (long long)(j0 + key) * pitch + (isv ? 256 : 128) + j * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(d)), "l"(src));
+      } else {
+        *reinterpret_cast<uint4*>(d) = make_uint4(0, 0, 0, 0);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // Q tile (zero rows past N)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int v = tid + i * 128, row = v >> 2, j = v & 3;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (q0 + row < N) val = *reinterpret_cast<const uint4*>(base + (long long)(q0 + row) * pitch + j * 8);
+    *reinterpret_cast<uint4*>(Qs + row * FA_P + j * 8) = val;
+  }
+  load_kv(0, 0);
+  __syncthreads();
+  // A fragments of Q: rows warp*16 + (0..15), two k-steps of 16 d's
+  uint32_t qa[2][4];
+  {
+    const int mi = lane >> 3, r8 = lane & 7;  // matrices: (rows 0-7, d 0-7) (rows 8-15, d 0-7) (rows 0-7, d 8-15) (rows 8-15, d 8-15)
+    const uint32_t qb = (uint32_t)__cvta_generic_to_shared(Qs);
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4(qb + (uint32_t)(((warp * 16 + (mi & 1) * 8 + r8) * FA_P + ks * 16 + (mi >> 1) * 8) * 2), qa[ks][0], qa[ks][1], qa[ks][2],
+              qa[ks][3]);
+  }
+  float o[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) o[i][j] = 0.f;
+  float m_lo = -INFINITY, m_hi = -INFINITY, l_lo = 0.f, l_hi = 0.f;
+  const float SC = 0.17677669529663687f * 1.4426950408889634f;  // 32^-0.5 * log2(e): softmax in base 2
+  const int nblk = (N + FA_K - 1) / FA_K;
+  for (int kb = 0; kb < nblk; ++kb) {
+    const int buf = kb & 1, j0 = kb * FA_K;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();  // tile[buf] landed; everyone finished with tile[buf^1]
+    if (kb + 1 < nblk) load_kv(j0 + FA_K, buf ^ 1);
+    const uint32_t kbase = (uint32_t)__cvta_generic_to_shared(Ks[buf]);
+    const uint32_t vbase = (uint32_t)__cvta_generic_to_shared(Vs[buf]);
+    const int mi = lane >> 3, r8 = lane & 7;
+    // ---- S = Q K^T: 8 n-tiles of 8 keys
+    float sc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      sc[nt][0] = sc[nt][1] = sc[nt][2] = sc[nt][3] = 0.f;
+      uint32_t b0, b1, b2, b3;  // (keys, d 0-7) (keys, d 8-15) (keys, d 16-23) (keys, d 24-31)
+      ldsm_x4(kbase + (uint32_t)(((nt * 8 + r8) * FA_P + mi * 8) * 2), b0, b1, b2, b3);
+      mma_bf16_16816(sc[nt], qa[0][0], qa[0][1], qa[0][2], qa[0][3], b0, b1);
+      mma_bf16_16816(sc[nt], qa[1][0], qa[1][1], qa[1][2], qa[1][3], b2, b3);
+    }
+    // ---- mask keys past N, scale, row max
+    const int g = lane >> 2, t4 = lane & 3;
+    float mx_lo = -INFINITY, mx_hi = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      const int key = j0 + nt * 8 + t4 * 2;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const bool ok = key + (e & 1) < N;
+        sc[nt][e] = ok ? sc[nt][e] * SC : -INFINITY;
+      }
+      mx_lo = fmaxf(mx_lo, fmaxf(sc[nt][0], sc[nt][1]));
+      mx_hi = fmaxf(mx_hi, fmaxf(sc[nt][2], sc[nt][3]));
+    }
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 1));
+    mx_lo = fmaxf(mx_lo, __shfl_xor_sync(0xffffffffu, mx_lo, 2));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 1));
+    mx_hi = fmaxf(mx_hi, __shfl_xor_sync(0xffffffffu, mx_hi, 2));
+    const float mn_lo = fmaxf(m_lo, mx_lo), mn_hi = fmaxf(m_hi, mx_hi);   // finite: every block holds >= 1 valid key
+    const float al_lo = exp2f(m_lo - mn_lo), al_hi = exp2f(m_hi - mn_hi); // 0 on the first block
+    m_lo = mn_lo; m_hi = mn_hi;
+    // ---- P = exp2(S - m) as bf16 A fragments; row sums of the ROUNDED values the MMA consumes
+    uint32_t pa[4][4];
+    float ps_lo = 0.f, ps_hi = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int nt = kk * 2 + half;
+        const float p0 = exp2f(sc[nt][0] - mn_lo), p1 = exp2f(sc[nt][1] - mn_lo);
+        const float p2 = exp2f(sc[nt][2] - mn_hi), p3 = exp2f(sc[nt][3] - mn_hi);
+        const uint32_t lo2 = pack_bf16x2(p0, p1), hi2 = pack_bf16x2(p2, p3);
+        pa[kk][half * 2 + 0] = lo2;
+        pa[kk][half * 2 + 1] = hi2;
+        const __nv_bfloat162 l2 = *reinterpret_cast<const __nv_bfloat162*>(&lo2), h2 = *reinterpret_cast<const __nv_bfloat162*>(&hi2);
+        ps_lo += __low2float(l2) + __high2float(l2);
+        ps_hi += __low2float(h2) + __high2float(h2);
+      }
+    }
+    ps_lo += __shfl_xor_sync(0xffffffffu, ps_lo, 1);
+    ps_lo += __shfl_xor_sync(0xffffffffu, ps_lo, 2);
+    ps_hi += __shfl_xor_sync(0xffffffffu, ps_hi, 1);
+    ps_hi += __shfl_xor_sync(0xffffffffu, ps_hi, 2);
+    l_lo = l_lo * al_lo + ps_lo;
+    l_hi = l_hi * al_hi + ps_hi;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { o[nt][0] *= al_lo; o[nt][1] *= al_lo; o[nt][2] *= al_hi; o[nt][3] *= al_hi; }
+    // ---- O += P V: 4 k-steps of 16 keys, 4 n-tiles of 8 d's
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+#pragma unroll
+      for (int np = 0; np < 2; ++np) {
+        uint32_t b0, b1, b2, b3;  // (k 0-7, n 0-7) (k 8-15, n 0-7) (k 0-7, n 8-15) (k 8-15, n 8-15) after transpose
+        ldsm_x4_trans(vbase + (uint32_t)(((kk * 16 + (mi & 1) * 8 + r8) * FA_P + np * 16 + (mi >> 1) * 8) * 2), b0, b1, b2, b3);
+        mma_bf16_16816(o[np * 2], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b0, b1);
+        mma_bf16_16816(o[np * 2 + 1], pa[kk][0], pa[kk][1], pa[kk][2], pa[kk][3], b2, b3);
+      }
+    }
+  }
+  // ---- normalise and store rows g / g+8
+  const int g = lane >> 2, t4 = lane & 3;
+  const float inv_lo = 1.0f / l_lo, inv_hi = 1.0f / l_hi;
+  const int r_lo = q0 + warp * 16 + g, r_hi = r_lo + 8;
+#pragma unroll
+  for (int nt = 0; nt < 4; ++nt) {
+    const int col = h * 32 + nt * 8 + t4 * 2;
+    if (r_lo < N)
+      *reinterpret_cast<__nv_bfloat162*>(hidden + ((long long)b * N + r_lo) * hid_pitch + col) = __floats2bfloat162_rn(o[nt][0] * inv_lo, o[nt][1] * inv_lo);
+    if (r_hi < N)
+      *reinterpret_cast<__nv_bfloat162*>(hidden + ((long long)b * N + r_hi) * hid_pitch + col) = __floats2bfloat162_rn(o[nt][2] * inv_hi, o[nt][3] * inv_hi);
+  }
+}
+
 template <typename T>
 void launch_fullattn(const T* qkv, int qkv_pitch, T* hidden, int hid_pitch, int B, int N, cudaStream_t st) {
   pdl_launch(fullattn_kernel<T>, dim3((N + 127) / 128, B * 4), 128, 0, st, qkv, qkv_pitch, hidden, hid_pitch, N);
+}
+template <>
+void launch_fullattn<bf16>(const bf16* qkv, int qkv_pitch, bf16* hidden, int hid_pitch, int B, int N, cudaStream_t st) {
+  static const bool force_scalar = getenv("IRSDE_FULLATTN_SCALAR") && getenv("IRSDE_FULLATTN_SCALAR")[0] == '1';
+  if (!force_scalar && qkv_pitch % 8 == 0 && hid_pitch % 2 == 0 && ((uintptr_t)qkv % 16) == 0 && ((uintptr_t)hidden % 4) == 0)
+    pdl_launch(fullattn_mma_kernel, dim3((N + FA_Q - 1) / FA_Q, B * 4), 128, 0, st, qkv, qkv_pitch, hidden, hid_pitch, N);
+  else
+    pdl_launch(fullattn_kernel<bf16>, dim3((N + 127) / 128, B * 4), 128, 0, st, qkv, qkv_pitch, hidden, hid_pitch, N);
 }
 template void launch_fullattn<float>(const float*, int, float*, int, int, int, cudaStream_t);
 template void launch_fullattn<bf16>(const bf16*, int, bf16*, int, int, int, cudaStream_t);

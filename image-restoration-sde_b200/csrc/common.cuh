@@ -168,6 +168,8 @@ void launch_set_step(StepState* st_dev, int t, int i, const float* z, unsigned l
                      const unsigned long long* uids, cudaStream_t st);
 void launch_noise_state(const float* mu, float* out, long long n, float max_sigma, uint64_t seed, long long img_elems,
                         uint64_t uid_base, const unsigned long long* uids, cudaStream_t st);
+void launch_random_states(const float* x0, const float* mu, const float* noise, const float* w, const float* sb, float* out,
+                          int B, long long img_elems, cudaStream_t st);
 // layout helpers for the tensor-core path
 template <typename T>
 void launch_space_to_depth(const T* in, int in_pitch, T* out, int B, int H, int W, int C, cudaStream_t st);

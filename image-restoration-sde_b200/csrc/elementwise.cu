@@ -389,6 +389,41 @@ void launch_space_to_depth(const T* in, int in_pitch, T* out, int B, int H, int 
   pdl_launch(s2d_kernel<T>, (unsigned)((total + 255) / 256), 256, 0, st, in, in_pitch, out, B, H, W, C);
 }
 // =============================================================================================
+// training-time state sampler (sde_utils.py:343-358): x_t = noise * sigma_bar[t_b] + (mu + (x0 - mu) * exp(-Theta[t_b] dt)),
+// one timestep per image; w[b] / sb[b] are the per-image scalars, the arithmetic follows the reference's op order with
+// round-to-nearest intrinsics (no FMA contraction), so the result is bit-identical to the torch expression.
+// =============================================================================================
+__global__ void random_states_kernel(const float* __restrict__ x0, const float* __restrict__ mu, const float* __restrict__ noise,
+                                     const float* __restrict__ w, const float* __restrict__ sb, float* __restrict__ out,
+                                     long long n, long long img_elems) {
+  long long i0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= n) return;
+  const bool vec = ((((uintptr_t)x0 | (uintptr_t)mu | (uintptr_t)noise | (uintptr_t)out) & 15) == 0) && (img_elems % 4 == 0) && i0 + 3 < n;
+  if (vec) {
+    const int b = (int)(i0 / img_elems);
+    const float wb = w[b], sbb = sb[b];
+    const float4 a = *reinterpret_cast<const float4*>(x0 + i0), m = *reinterpret_cast<const float4*>(mu + i0);
+    const float4 z = *reinterpret_cast<const float4*>(noise + i0);
+    float4 o;
+    o.x = __fadd_rn(__fmul_rn(z.x, sbb), __fadd_rn(m.x, __fmul_rn(__fsub_rn(a.x, m.x), wb)));
+    o.y = __fadd_rn(__fmul_rn(z.y, sbb), __fadd_rn(m.y, __fmul_rn(__fsub_rn(a.y, m.y), wb)));
+    o.z = __fadd_rn(__fmul_rn(z.z, sbb), __fadd_rn(m.z, __fmul_rn(__fsub_rn(a.z, m.z), wb)));
+    o.w = __fadd_rn(__fmul_rn(z.w, sbb), __fadd_rn(m.w, __fmul_rn(__fsub_rn(a.w, m.w), wb)));
+    *reinterpret_cast<float4*>(out + i0) = o;
+    return;
+  }
+  for (long long i = i0; i < n && i < i0 + 4; ++i) {
+    const int b = (int)(i / img_elems);
+    out[i] = __fadd_rn(__fmul_rn(noise[i], sb[b]), __fadd_rn(mu[i], __fmul_rn(__fsub_rn(x0[i], mu[i]), w[b])));
+  }
+}
+void launch_random_states(const float* x0, const float* mu, const float* noise, const float* w, const float* sb, float* out,
+                          int B, long long img_elems, cudaStream_t st) {
+  const long long n = (long long)B * img_elems, groups = (n + 3) / 4;
+  random_states_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, st>>>(x0, mu, noise, w, sb, out, n, img_elems);
+}
+
+// =============================================================================================
 // fp32x3 operand split: hi = rn_tf32(x) (10-bit mantissa, low 13 bits zero), lo = rn_tf32(x - hi).  x - hi is exact in
 // fp32, so x = hi + lo + r with |r| <= 2^-22 |x|: three tf32 MMAs (hi*hi + lo*hi + hi*lo) reproduce the fp32 product to
 // 2^-21 relative.  Both parts carry explicit zero low bits, so the result does not depend on how the tensor core

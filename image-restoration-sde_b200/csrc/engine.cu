@@ -1925,6 +1925,16 @@ int irsde_noise_state_images(irsde_ctx* ctx, const float* mu, float* out, int32_
   return IRSDE_OK;
 }
 
+int irsde_random_states(const float* x0, const float* mu, const float* noise, const float* w, const float* sigma_bar, float* out,
+                        int32_t B, int64_t image_elems, void* stream) {
+  if (!x0 || !mu || !noise || !w || !sigma_bar || !out || B < 1 || image_elems < 1)
+    return fail(nullptr, IRSDE_ERR_INVALID, "bad argument to irsde_random_states");
+  launch_random_states(x0, mu, noise, w, sigma_bar, out, B, image_elems, (cudaStream_t)stream);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(nullptr, IRSDE_ERR_CUDA, std::string("random_states: ") + cudaGetErrorString(e));
+  return IRSDE_OK;
+}
+
 int irsde_set_image_base(irsde_ctx* ctx, uint64_t first_image_uid) {
   if (!ctx) return fail(ctx, IRSDE_ERR_INVALID, "null ctx");
   ctx->image_base = first_image_uid;

@@ -19,7 +19,24 @@ from .unet import ConditionalUNet
 def _unwrap(model):
     # DataParallel / DistributedDataParallel hand us a wrapper (models/denoising_model.py:37-42,
     # test.py:71); the native sampler owns batching itself, so use the underlying module.
-    return getattr(model, "module", model)
+    m = getattr(model, "module", model)
+    if m is None or isinstance(m, ConditionalUNet):
+        return m
+    # A foreign nn.Module with the reference ConditionalUNet's state-dict layout (e.g. the reference's own PyTorch class
+    # being trained by autograd in train.py): sample through a native shadow that re-reads its parameters (unet.adopt).
+    # Opt out with IRSDE_B200_ADOPT=0; modules in training mode are left alone (autograd needs the PyTorch forward).
+    if isinstance(m, torch.nn.Module) and os.environ.get("IRSDE_B200_ADOPT", "1") != "0" and not m.training:
+        sh = getattr(m, "_irsde_b200_shadow", None)
+        if sh is None:
+            from .unet import adopt
+            sh = adopt(m) or False
+            try:
+                object.__setattr__(m, "_irsde_b200_shadow", sh)
+            except Exception:
+                pass
+        if sh:
+            return sh
+    return m
 
 
 class _SDEBase:
@@ -347,16 +364,32 @@ class IRSDE(_SDEBase):
         return torch.exp(-self.thetas_cumsum[t] * self.dt)
 
     def generate_random_states(self, x0, mu):
+        """Training-time state sampler (sde_utils.py:343-358; train.py:236).  Same generator calls as the reference
+        (one CPU randint for the timesteps, one randn_like on the device); on a CUDA device the mean-reversion + noising is
+        ONE fused kernel (irsde_random_states) that reproduces the torch expression bit for bit."""
         x0 = x0.to(self.device)
         mu = mu.to(self.device)
         self.set_mu(mu)
         batch = x0.shape[0]
         timesteps = torch.randint(1, self.T + 1, (batch, 1, 1, 1)).long()
-        state_mean = self.mu_bar(x0, timesteps)
-        noises = torch.randn_like(state_mean)
-        noise_level = self.sigma_bar(timesteps)
-        noisy_states = noises * noise_level + state_mean
-        return timesteps, noisy_states.to(torch.float32)
+        if not (x0.is_cuda and x0.dtype == torch.float32 and mu.shape == x0.shape):
+            state_mean = self.mu_bar(x0, timesteps)
+            noises = torch.randn_like(state_mean)
+            noise_level = self.sigma_bar(timesteps)
+            noisy_states = noises * noise_level + state_mean
+            return timesteps, noisy_states.to(torch.float32)
+        noises = torch.randn_like(x0)
+        t = timesteps.reshape(-1).to(x0.device)
+        w = torch.exp(-self.thetas_cumsum[t] * self.dt).float().contiguous()     # the reference's per-image scalars, same ops
+        sb = self.sigma_bars[t].float().contiguous()
+        x0c, muc = x0.contiguous(), mu.contiguous()
+        out = torch.empty_like(x0c)
+        p = lambda a: ctypes.c_void_p(a.data_ptr())
+        with torch.cuda.device(x0.device):
+            st = torch.cuda.current_stream().cuda_stream
+            _lib.check(_lib.load().irsde_random_states(p(x0c), p(muc), p(noises), p(w), p(sb), p(out), batch, x0c[0].numel(),
+                                                       ctypes.c_void_p(st)))
+        return timesteps, out
 
     def noise_state(self, tensor):
         # called on CPU tensors by test.py:104 before feed_data: plain torch, like the reference

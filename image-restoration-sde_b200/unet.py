@@ -147,9 +147,12 @@ class ConditionalUNet(nn.Module):
         return self._ctx
 
     def sync_weights(self, device=None):
-        """Upload parameters to the native context if they changed since the last upload."""
+        """Upload parameters to the native context if they changed since the last upload.  ``_source`` (set by ``adopt``)
+        names another module that owns the parameters: e.g. the reference's own PyTorch ConditionalUNet while it is being
+        trained by autograd - the native network then shadows it (same state-dict names) for validation sampling."""
         import ctypes
-        params = dict(self.named_parameters())
+        src = getattr(self, "_source", None)
+        params = dict((src if src is not None else self).named_parameters())
         dev = device or next(iter(params.values())).device
         ctx = self._context(dev)
         sig = tuple((p.data_ptr(), p._version) for p in params.values())
@@ -253,3 +256,50 @@ class DenoisingUNet(ConditionalUNet):
     @torch.no_grad()
     def forward(self, x, time):
         return self._run(x, None, time)
+
+
+def infer_unet_config(state_dict):
+    """(in_nc, out_nc, nf, ch_mult, variant) of a ConditionalUNet state dict in the reference's naming, or None."""
+    try:
+        sd = state_dict
+        nf = sd["init_conv.weight"].shape[0]
+        cin0 = sd["init_conv.weight"].shape[1]
+        out_nc = sd["final_conv.weight"].shape[0]
+        variant = "denoising" if "mid_attn.fn.fn.to_out.weight" in sd else "conditional"
+        in_nc = cin0 // 2 if variant == "conditional" else cin0
+        mult, i = [], 0
+        while ("downs.%d.3.weight" % i) in sd:
+            mult.append(sd["downs.%d.3.weight" % i].shape[0] // nf)
+            i += 1
+        if not mult:
+            return None
+        return in_nc, out_nc, nf, mult, variant
+    except Exception:
+        return None
+
+
+def adopt(module, precision=None):
+    """Native shadow of a foreign ``nn.Module`` that has the reference ConditionalUNet's state-dict layout (the
+    reference's own PyTorch class, codes/config/*/models/modules/DenoisingUNet_arch.py): the shadow keeps no weights of its
+    own - every call re-reads the foreign module's parameters when their versions changed (optimizer steps bump them) -
+    so `train.py` can keep training the PyTorch module with autograd while validation sampling (train.py:261-281) runs on
+    the native kernels.  Returns None when the state dict is not a ConditionalUNet."""
+    sd = {k: v for k, v in module.state_dict().items()}
+    cfg = infer_unet_config(sd)
+    if cfg is None:
+        return None
+    in_nc, out_nc, nf, mult, variant = cfg
+    plain = mult == [2 ** (i + 1) for i in range(len(mult))]
+    if variant == "denoising":
+        if not plain:
+            return None
+        net = DenoisingUNet(in_nc, out_nc, nf, depth=len(mult), precision=precision)
+    else:
+        net = ConditionalUNet(in_nc, out_nc, nf, depth=len(mult), precision=precision, ch_mult=None if plain else mult)
+    if list(net._shapes.keys()) != list(sd.keys()) or any(tuple(sd[k].shape) != tuple(v) for k, v in net._shapes.items()):
+        return None
+    for p in net.parameters():       # the shadow's own tensors are never used: do not keep a second copy of the weights
+        p.data = torch.empty(0)
+    net._source = module
+    net.eval()
+    return net

@@ -160,6 +160,12 @@ int irsde_noise_state(irsde_ctx* ctx, const float* mu, float* out, int64_t n, ui
 /* Same for a batch [B][image_elems]: image b is drawn with uid = image base + b. */
 int irsde_noise_state_images(irsde_ctx* ctx, const float* mu, float* out, int32_t B, int64_t image_elems, uint64_t seed,
                              void* stream);
+/* Training-time state sampler `IRSDE.generate_random_states` (sde_utils.py:343-358; train.py:236): one fused pass
+ * x_t = noise * sigma_bar[t_b] + (mu + (x0 - mu) * w[b]) with per-image scalars w[b] = exp(-thetas_cumsum[t_b] dt) and
+ * sigma_bar[b] (device arrays of B floats); bit-identical to the reference's torch expression.  Stateless (no ctx). */
+int irsde_random_states(const float* x0, const float* mu, const float* noise, const float* w, const float* sigma_bar, float* out,
+                        int32_t B, int64_t image_elems, void* stream);
+
 /* The in-kernel Philox (irsde_reverse with z == NULL, irsde_noise_state*) is keyed by
  * (seed, image uid, timestep, element index inside the image), uid = image base + position in the batch.
  * An image's noise therefore does not depend on the batch it is processed in, its position, or the rank that

@@ -221,21 +221,23 @@ def test_unet_nf64_forward_fp32_vs_oracle(lib):
     assert (y - yo).abs().max().item() < 1e-4, (y - yo).abs().max().item()
 
 
-def test_denoising_unet_bf16_vs_oracle(lib, capsys):
-    """bf16 denoising-sde network (full softmax Attention at mid_attn, N = 1024 keys at 128^2 / depth 2 ... here nf=32,
-    depth=3 on 128^2 -> mid level 32^2 = 1024 tokens): per-layer report incl. the attention output."""
+@pytest.mark.parametrize("nf,depth,H,W", [(32, 3, 128, 128), (16, 2, 50, 38), (16, 2, 256, 256)],
+                         ids=["N=1024 keys", "ragged N=520 keys", "N=4096 keys"])
+def test_denoising_unet_bf16_vs_oracle(lib, capsys, nf, depth, H, W):
+    """bf16 denoising-sde network: full softmax Attention at mid_attn on the tensor cores (fullattn_mma_kernel, flash
+    attention by mma.sync) - 1024 keys (the 256^2 / depth-4 mid level's token count), a ragged 520-key case (key masking,
+    partial query block) and 4096 keys (the 512^2 count): per-layer report incl. the attention output."""
     dev = _dev()
-    nf, depth = 32, 3
     P = O.make_weights(3, 3, nf, depth, variant="denoising", seed=4)
     net = lib.DenoisingUNet(3, 3, nf, depth=depth, precision="bf16")
     net.load_state_dict(P, strict=True)
     net = net.to(dev)
     g = torch.Generator().manual_seed(5)
-    x = torch.rand(2, 3, 128, 128, generator=g) + torch.randn(2, 3, 128, 128, generator=g) * (50 / 255)
+    x = torch.rand(2, 3, H, W, generator=g) + torch.randn(2, 3, H, W, generator=g) * (50 / 255)
     yo, rows = _layer_report(net, P, x, None, 21, nf, depth, variant="denoising")
     y = net(x.to(dev), 21).cpu()
     with capsys.disabled():
-        print("\nper-layer bf16 denoising-sde UNet vs fp32 oracle (nf=32 depth=3, 2x3x128x128)")
+        print("\nper-layer bf16 denoising-sde UNet vs fp32 oracle (nf=%d depth=%d, 2x3x%dx%d)" % (nf, depth, H, W))
         for key, dmax, rmax, rel in rows:
             if "mid" in key:
                 print("  %-38s max|d| %.3e  max|ref| %.3e  rel-rms %.2e" % (key, dmax, rmax, rel))

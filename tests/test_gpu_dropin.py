@@ -109,3 +109,67 @@ def test_reference_test_py_runs_unchanged(tmp_path, mode):
     assert worst <= 1, "restored images differ by %d grey levels" % worst
     # both logs report the same metrics line format (the script ran to its end in both arms)
     assert "Average PSNR/SSIM" in out_native and "Average PSNR/SSIM" in out_ref
+
+
+def test_validation_sampling_adopts_reference_module_during_training():
+    """SURVEY 8 f-4 (train.py:214-215,236,261-281): the reference's PyTorch ConditionalUNet keeps being trained by autograd;
+    `sde.set_model(DataParallel(net))` + `model.eval()` + `sde.reverse_posterior(...)` must sample through the native
+    kernels with the module's CURRENT weights (before and after an optimizer step), and `generate_random_states` must give
+    the reference's states bit for bit."""
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    if not os.path.exists(os.path.join(REF, ".staged")):
+        pytest.skip("baseline/_ref not staged")
+    sys.path.insert(0, os.path.join(ROOT, "baseline"))
+    sys.path.insert(0, ROOT)
+    import ref_loader
+    rutil, rmods = ref_loader.load("deraining")
+    import irsde_b200
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    ref_net = rmods.ConditionalUNet(3, 3, 16, 2).to(dev)
+    wrapped = torch.nn.DataParallel(ref_net, device_ids=[0])
+    ours = irsde_b200.IRSDE(10, 12, schedule="cosine", eps=0.005, device=dev)
+    theirs = rutil.IRSDE(max_sigma=10, T=12, schedule="cosine", eps=0.005, device=dev)
+    ours.set_model(wrapped)
+    theirs.set_model(wrapped)
+    g = torch.Generator().manual_seed(1)
+    GT, LQ = torch.rand(2, 3, 24, 40, generator=g), torch.rand(2, 3, 24, 40, generator=g)
+
+    # ---- train.py:236  generate_random_states: same generator calls, bit-identical states
+    torch.manual_seed(5)
+    t_ref, s_ref = theirs.generate_random_states(x0=GT, mu=LQ)
+    torch.manual_seed(5)
+    t_our, s_our = ours.generate_random_states(x0=GT, mu=LQ)
+    assert torch.equal(t_ref, t_our) and torch.equal(s_ref, s_our)
+
+    opt = torch.optim.SGD(ref_net.parameters(), lr=1e-2)
+
+    def validate():
+        wrapped.eval()
+        outs = []
+        for sde in (theirs, ours):
+            sde.set_mu(LQ.to(dev))
+            torch.manual_seed(9)
+            with torch.no_grad():
+                outs.append(sde.reverse_posterior(LQ.to(dev) + 0.03))
+        wrapped.train()
+        return outs
+
+    a_ref, a_our = validate()
+    assert (a_ref - a_our).abs().max().item() < 1e-3
+    shadow = getattr(ref_net, "_irsde_b200_shadow", None)
+    assert shadow is not None and shadow is not False and shadow.launch_count() > 0     # the native kernels ran
+    # ---- one real training step through the reference's autograd forward (train.py:239 optimize_parameters)
+    ref_net.train()
+    ts, states = theirs.generate_random_states(x0=GT, mu=LQ)
+    noise = theirs.noise_fn(states, ts.squeeze().to(dev))
+    loss = noise.pow(2).mean()
+    loss.backward()
+    opt.step()
+    b_ref, b_our = validate()
+    assert (b_ref - b_our).abs().max().item() < 1e-3           # the shadow picked up the updated weights
+    assert (b_ref - a_ref).abs().max().item() > 1e-4           # and the step did change the result

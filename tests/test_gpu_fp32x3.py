@@ -172,7 +172,20 @@ def test_nf64_chain_fp32x3_vs_fp32_and_oracle(lib, capsys):
     xt = cond + torch.randn(1, 3, 256, 256, generator=g) * (10 / 255)
     yo = O.unet_forward(P, xt, cond, 57, nf, depth)
     d_fwd = _maxdiff(net(xt.to(dev), cond.to(dev), 57), yo)
+    # per-layer relative RMS error of both fp32-accurate modes against the CPU oracle
+    from test_gpu_bench_shapes import _layer_report
+    _, rows3 = _layer_report(net, P, xt, cond, 57, nf, depth)
     del net
+    net1 = lib.ConditionalUNet(3, 3, nf, depth=depth, precision="fp32")
+    net1.load_state_dict(P, strict=True)
+    net1 = net1.to(dev)
+    _, rows1 = _layer_report(net1, P, xt, cond, 57, nf, depth)
+    del net1
+    with capsys.disabled():
+        print("\nper-layer rel-rms vs fp32 CPU oracle (nf=64 depth=4, 1x3x256x256): fp32 SIMT | fp32x3 tensor-core")
+        for (k1, _, _, r1), (k3, _, _, r3) in zip(rows1, rows3):
+            if "block2" in k1 or "3." in k1 or "norm+res" in k1:
+                print("  %-38s %.2e | %.2e" % (k1, r1, r3))
     raw = _chain_pair(lib, ("fp32", "fp32x3"), assisted=False)
     ast = _chain_pair(lib, ("fp32", "fp32x3"), assisted=True)
     l1, d1, p1, _ = _drift_line("T=100 raw random-weight chain, fp32x3 vs fp32", raw["fp32x3"], raw["fp32"])

@@ -636,3 +636,22 @@ def test_unet_ch_mult_variant(lib, precision):
     tol = 1e-4 if precision == "fp32" else 4e-2 * g["y_int"].abs().max().item()
     assert _maxdiff(net(g["x"].to(dev), g["cond"].to(dev), g["t_int"]), g["y_int"]) < tol
     assert _maxdiff(net(g["x"].to(dev), g["cond"].to(dev), g["t_vec"]), g["y_vec"]) < tol
+
+
+def test_generate_random_states_bit_exact(lib):
+    """Training-time state sampler (sde_utils.py:343-358): the fused kernel == the reference's torch expression, bit for bit,
+    also for image sizes that are not a multiple of 4 elements."""
+    dev = _dev()
+    sde = lib.IRSDE(25, 100, eps=0.005, device=dev)
+    for shape in ((4, 3, 16, 20), (3, 3, 9, 7), (1, 1, 5, 5)):
+        g = torch.Generator().manual_seed(sum(shape))
+        x0, mu = torch.rand(shape, generator=g), torch.rand(shape, generator=g)
+        torch.manual_seed(3)
+        ts, st = sde.generate_random_states(x0, mu)
+        torch.manual_seed(3)
+        t2 = torch.randint(1, sde.T + 1, (shape[0], 1, 1, 1)).long()
+        noises = torch.randn(shape, device=dev)
+        x0d, mud = x0.to(dev), mu.to(dev)
+        mean = mud + (x0d - mud) * torch.exp(-sde.thetas_cumsum[t2] * sde.dt)
+        ref = noises * sde.sigma_bars[t2] + mean
+        assert torch.equal(ts, t2) and torch.equal(st, ref)
