@@ -398,6 +398,7 @@ constexpr int PATCH_STRIDE = 24 * 1024;                // per-buffer stride (102
 // read 1024-byte-ALIGNED row windows of the same box (window dh starts (dh+1)*BW pixel rows in), so the A operand
 // is fetched 3x instead of 9x per 64-channel chunk with ordinary aligned UMMA descriptors, and one full/empty
 // barrier round covers 12 MMAs.
+constexpr int TF3_SEG = 8;  // fp32x3: k-iterations (of 32 channels, 12 MMAs each) accumulated in TMEM before a flush to registers
 constexpr int ROWS_A_SLOT = 20 * 1024;  // (8+2) rows x 16 px x 128 B (or 18 x 8 px for narrow images)
 
 // MODE 3 "fp32x3" (the fp32-accurate tensor-core mode, SURVEY 7 "Parity vs precision"): operands are fp32 tensors that were
@@ -637,34 +638,52 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       const uint32_t idesc = TF3 ? make_idesc_tf32(128, BN) : make_idesc_bf16(128, BN);
       int it = 0, lt = 0, pc = 0;
       long long w_full = 0, w_tempty = 0, t_start = clock64();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
+      if constexpr (TF3) {
+        // fp32x3: the K loop of a tile is cut into SEGMENTS of TF3_SEG k-iterations; each segment accumulates from zero in
+        // one of the two TMEM buffers and is handed to the epilogue warps, which sum the segments in fp32 registers with
+        // round-to-nearest adds.  Reason (measured, profiles/ + tests/test_gpu_fp32x3.py): the tensor core's accumulator
+        // update truncates, so a single TMEM accumulation over n MMAs drifts by ~n * 2^-26 relative - 3e-5 per layer at
+        // K = 13 824 (5 184 MMAs), 70x the error of the fp32 FMA path.  96 MMAs per segment keep it at ~1e-6.
+        int st = 0;  // segments issued by this CTA (TMEM buffer = st & 1)
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+          for (int k0 = 0; k0 < KI; k0 += TF3_SEG, ++st) {
+            const int acc = st & 1;
+            if (st >= 2) DBG_WAIT(w_tempty, &tempty_bar[acc], ((st >> 1) - 1) & 1);  // epilogue drained this buffer
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
+            const int k1 = k0 + TF3_SEG < KI ? k0 + TF3_SEG : KI;
+            for (int ki = k0; ki < k1; ++ki, ++it) {
+              const int s = it % STAGES;
+              DBG_WAIT(w_full, &full_bar[s], (it / STAGES) & 1);
+              tc_fence_after();
+              if (elect_one()) {
+                const uint64_t a_hi = make_sw128_desc(smem_u32(smem_a + (s * 2 + 0) * A_STAGE_BYTES));
+                const uint64_t a_lo = make_sw128_desc(smem_u32(smem_a + (s * 2 + 1) * A_STAGE_BYTES));
+                const uint64_t b_hi = make_sw128_desc(smem_u32(smem_b + (s * 2 + 0) * Cfg::B_STAGE_BYTES));
+                const uint64_t b_lo = make_sw128_desc(smem_u32(smem_b + (s * 2 + 1) * Cfg::B_STAGE_BYTES));
+                // the two small cross terms first, the dominant hi*hi product last
+#pragma unroll
+                for (int k = 0; k < 4; ++k)  // 4 x (K=8 tf32) per 32-channel chunk: +32 B inside the swizzle atom
+                  umma_tf32(tmem_d, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (ki > k0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, 1u);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, 1u);
+                umma_commit(&empty_bar[s]);
+              }
+              __syncwarp();
+            }
+            if (elect_one()) umma_commit(&tfull_bar[acc]);
+            __syncwarp();
+          }
+        }
+      }
+      for (int tile = blockIdx.x; tile < num_tiles && !TF3; tile += gridDim.x, ++lt) {
         const int acc = lt & 1;
         if (lt >= 2) DBG_WAIT(w_tempty, &tempty_bar[acc], ((lt >> 1) - 1) & 1);  // epilogue drained this buffer
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * BN);
-        if constexpr (TF3) {
-          for (int ki = 0; ki < KI; ++ki, ++it) {
-            const int s = it % STAGES;
-            DBG_WAIT(w_full, &full_bar[s], (it / STAGES) & 1);
-            tc_fence_after();
-            if (elect_one()) {
-              const uint64_t a_hi = make_sw128_desc(smem_u32(smem_a + (s * 2 + 0) * A_STAGE_BYTES));
-              const uint64_t a_lo = make_sw128_desc(smem_u32(smem_a + (s * 2 + 1) * A_STAGE_BYTES));
-              const uint64_t b_hi = make_sw128_desc(smem_u32(smem_b + (s * 2 + 0) * Cfg::B_STAGE_BYTES));
-              const uint64_t b_lo = make_sw128_desc(smem_u32(smem_b + (s * 2 + 1) * Cfg::B_STAGE_BYTES));
-              // the two small cross terms first, the dominant hi*hi product last
-#pragma unroll
-              for (int k = 0; k < 4; ++k)  // 4 x (K=8 tf32) per 32-channel chunk: +32 B inside the swizzle atom
-                umma_tf32(tmem_d, a_lo + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, (ki > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), b_lo + (uint64_t)(k * 2), idesc, 1u);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) umma_tf32(tmem_d, a_hi + (uint64_t)(k * 2), b_hi + (uint64_t)(k * 2), idesc, 1u);
-              umma_commit(&empty_bar[s]);
-            }
-            __syncwarp();
-          }
-        } else if constexpr (ROWS) {
+        if constexpr (ROWS) {
           const int nst = 3 * P.kchunks;
           for (int si = 0; si < nst; ++si, ++it) {
             const int s = it % STAGES;
@@ -751,6 +770,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     uint8_t* stg = smem_stg + (warp - 2) * 2048;
     long long w_tfull = 0, t_start = clock64();
     int lt = 0, epi_n0 = -1, epi_b = -1;
+    int seg_st = 0;  // fp32x3: K segments consumed by this warp (TMEM buffer = seg_st & 1)
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
       const TileCoord t = decode_tile(P, tile, tiles_m, BN);
       const int acc = lt & 1;
@@ -902,10 +922,43 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
         }
       };
 
+      constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp
+      if constexpr (TF3) {
+        // sum the tile's K segments in registers (IEEE round-to-nearest adds), then run the epilogue on the sums
+        float accf[NCH][32];
+#pragma unroll
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int j = 0; j < 32; ++j) accf[i][j] = 0.f;
+        for (int k0 = 0; k0 < KI; k0 += TF3_SEG, ++seg_st) {
+          const int sacc = seg_st & 1;
+          DBG_WAIT(w_tfull, &tfull_bar[sacc], (seg_st >> 1) & 1);
+          tc_fence_after();
+          const uint32_t tmem_seg = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sacc * BN);
+#pragma unroll
+          for (int i = 0; i < NCH; ++i) {
+            const int c0 = (2 * i + half) * 32;
+            if (c0 < BN) {
+              uint32_t v1[32];
+              tmem_ld32(tmem_seg + (uint32_t)c0, v1);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) accf[i][j] = __fadd_rn(accf[i][j], __uint_as_float(v1[j]));
+            }
+          }
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty_bar[sacc]);
+        }
+#pragma unroll
+        for (int i = 0; i < NCH; ++i) {
+          const int c0 = (2 * i + half) * 32;
+          if (c0 < BN && t.n0 + c0 < P.Cout) process(reinterpret_cast<uint32_t*>(accf[i]), c0);
+        }
+        continue;
+      }
       DBG_WAIT(w_tfull, &tfull_bar[acc], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp
       uint32_t v[2][32];
       if (half * 32 < BN) tmem_ld32_async(tmem_acc + (uint32_t)(half * 32), v[0]);
 #pragma unroll
