@@ -193,6 +193,55 @@ __device__ __forceinline__ void tmem_ld_wait(uint32_t v[32]) {
                : "memory");
 }
 
+// ---- CTA-pair (cta_group::2) variants: per-tap BN = 256 layers, opt-in / auto (g_pair) ----------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Executed by both CTAs of the pair: the data lands in the issuing CTA's shared memory, the transaction bytes are
+// counted on the LEADER's barrier (clearing the CTA-rank bit of the shared::cluster address selects the even CTA).
+constexpr uint32_t PAIR_PEER_MASK = 0xFEFFFFFFu;
+__device__ __forceinline__ void tma_load_5d_pair(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & PAIR_PEER_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_pair(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar) & PAIR_PEER_MASK), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+// one commit arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+// arrive on the LEADER's copy of a barrier from either CTA of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
+
 constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16
 
 template <int BN>
@@ -398,7 +447,7 @@ constexpr int PATCH_STRIDE = 24 * 1024;                // per-buffer stride (102
 // read 1024-byte-ALIGNED row windows of the same box (window dh starts (dh+1)*BW pixel rows in), so the A operand
 // is fetched 3x instead of 9x per 64-channel chunk with ordinary aligned UMMA descriptors, and one full/empty
 // barrier round covers 12 MMAs.
-constexpr int TF3_SEG = 8;  // fp32x3: k-iterations (of 32 channels, 12 MMAs each) accumulated in TMEM before a flush to registers
+constexpr int TF3_SEG = 2;  // fp32x3: k-iterations (of 32 channels, 12 MMAs each) accumulated in TMEM before a flush to registers
 constexpr int ROWS_A_SLOT = 20 * 1024;  // (8+2) rows x 16 px x 128 B (or 18 x 8 px for narrow images)
 
 // MODE 3 "fp32x3" (the fp32-accurate tensor-core mode, SURVEY 7 "Parity vs precision"): operands are fp32 tensors that were
@@ -406,16 +455,24 @@ constexpr int ROWS_A_SLOT = 20 * 1024;  // (8+2) rows x 16 px x 128 B (or 18 x 8
 // 128-byte swizzled row as 64 bf16 channels; per chunk the MMA warp issues A_hi*W_hi + A_lo*W_hi + A_hi*W_lo as three
 // groups of four tcgen05.mma.kind::tf32 (K=8) into the SAME fp32 TMEM accumulator (the dropped lo*lo term is 2^-22 relative).
 // The epilogue keeps everything in fp32 (IEEE SiLU, fp32 residual, fp32 NHWC / NCHW stores).
-template <int BN, int MODE>
+// CG = 2: CTA pair (cta_group::2) - a cluster of two CTAs computes a 256-pixel x 256-channel tile with M = 256 MMAs issued by
+// the leader; each CTA stages its own 128 pixels of A and HALF of the weight tile (32 KB instead of 48 KB per k-iteration
+// and SM: the BN = 256 layers were L2->smem feed bound, MMA warp ~40 % of the time on the `full` barrier).
+template <int BN, int MODE, int CG = 1>
 struct TcCfgP {
   static constexpr bool PATCH = MODE == 1;
   static constexpr bool ROWS = MODE == 2;
   static constexpr bool TF3 = MODE == 3;
-  static constexpr int B_STAGE_BYTES = BN * 128;
+  static constexpr int B_STAGE_BYTES = BN * 128 / CG;
   // non-PATCH: G consecutive k-iterations (64-channel chunks) share one full/empty barrier round, which amortises the
   // mbarrier wait + tcgen05.commit of the single MMA-issuing thread over 4*G MMAs (matters for narrow N tiles)
   static constexpr int G = 1;  // measured: G=2 trades issue overhead for coarser prefetch granularity; no net gain
-  static constexpr int STAGES = TF3 ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
+  // Epilogue staging for the TMA stores: one 2 KB tile per epilogue warp.  (Two tiles per warp - so that a warp need not
+  // wait for its previous bulk store to finish reading the tile - were measured in round 2, same-box ABAB: no change;
+  // the store-heavy 1x1 convs are bound by L2 traffic (A re-read per N tile + weight tile re-fetched per output tile),
+  // not by the store latency.  STG_BUFS = 2 still works where shared memory allows it.)
+  static constexpr int STG_BUFS = TF3 ? 0 : 1;
+  static constexpr int STAGES = CG == 2 ? 6 : TF3 ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
                                 : ROWS ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
                                        : (PATCH ? (BN == 256 ? 4 : (BN == 128 ? 8 : 12)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
   static constexpr int BSUB = ROWS ? 3 : (TF3 ? 2 : 1);  // weight tiles per stage
@@ -423,8 +480,9 @@ struct TcCfgP {
   static constexpr int A_BYTES = TF3 ? STAGES * 2 * A_STAGE_BYTES
                                      : (ROWS ? STAGES * ROWS_A_SLOT : (PATCH ? 2 * PATCH_STRIDE : STAGES * G * A_STAGE_BYTES));
   static constexpr int EPI_FLOATS = 3 * BN;
-  static constexpr int STG_BYTES = TF3 ? 0 : 8 * 2048;  // per epilogue warp: one 32 rows x 64 B staging tile for TMA stores
+  static constexpr int STG_BYTES = STG_BUFS * 8 * 2048;  // per epilogue warp: STG_BUFS 32 rows x 64 B staging tiles for TMA stores
   static constexpr int SMEM_BYTES = 1024 + A_BYTES + STAGES * G * BSUB * B_STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 512;
+  static_assert(SMEM_BYTES <= 232448, "over the 227 KB per-CTA shared memory limit");
   static constexpr int TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
 };
 
@@ -454,6 +512,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, const void*
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 struct TileCoord {
@@ -464,6 +523,28 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
   int m_idx;
   if (P.n_fast) { m_idx = tile / P.tiles_n; t.n0 = (tile - m_idx * P.tiles_n) * BN; }
   else { m_idx = tile % tiles_m; t.n0 = (tile / tiles_m) * BN; }
+  const int tw_i = m_idx % P.tilesW; m_idx /= P.tilesW;
+  const int th_i = m_idx % P.tilesH; m_idx /= P.tilesH;
+  t.b = m_idx % P.B;
+  t.phase = m_idx / P.B;
+  t.py = t.phase >> 1; t.px = t.phase & 1;
+  t.h0 = th_i * P.BH; t.w0 = tw_i * P.BW;
+  return t;
+}
+
+// CTA pair: pair tile `pt` covers the m-tiles 2*mp and 2*mp+1 (one per CTA rank) of one N tile.  An odd tail leaves the
+// second CTA without pixels: it still runs the whole protocol on an out-of-range image index (TMA loads zero-fill,
+// TMA stores are clipped).
+__device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& P, int pt, int rank, int tiles_m, int BN) {
+  const int pairs_m = (tiles_m + 1) >> 1;
+  const int mp = pt % pairs_m;
+  int m_idx = 2 * mp + rank;
+  TileCoord t;
+  t.n0 = (pt / pairs_m) * BN;
+  if (m_idx >= tiles_m) {
+    t.b = P.B; t.phase = 0; t.py = 0; t.px = 0; t.h0 = 0; t.w0 = 0;
+    return t;
+  }
   const int tw_i = m_idx % P.tilesW; m_idx /= P.tilesW;
   const int th_i = m_idx % P.tilesH; m_idx /= P.tilesH;
   t.b = m_idx % P.B;
@@ -484,17 +565,18 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
     }                                           \
   } while (0)
 
-template <int BN, int MODE>
+template <int BN, int MODE, int CG = 1>
 __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                  const __grid_constant__ OutMaps map_o,
                                                                  const __grid_constant__ TcParams P, int tiles_m,
                                                                  int num_tiles) {
-  using Cfg = TcCfgP<BN, MODE>;
+  using Cfg = TcCfgP<BN, MODE, CG>;
   constexpr bool PATCH = Cfg::PATCH;
   constexpr bool ROWS = Cfg::ROWS;
   constexpr bool TF3 = Cfg::TF3;
   constexpr int STAGES = Cfg::STAGES;
+  static_assert(CG == 1 || (CG == 2 && MODE == 0 && BN == 256), "the CTA-pair variant exists for per-tap mode, BN = 256");
   pdl_trigger();  // the next kernel may be scheduled; this one's prologue below touches no global memory
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -513,6 +595,14 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KI = P.ntaps * P.kchunks;
+  // CTA pair (CG == 2): blockIdx.x = 2 * cluster + rank; `num_tiles` counts pair tiles; both CTAs walk the same pair tiles
+  const int crank = CG == 2 ? (int)cluster_ctarank() : 0;
+  const int tile_first = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_coord = [&](int tile) -> TileCoord {
+    if constexpr (CG == 2) return decode_pair_tile(P, tile, crank, tiles_m, BN);
+    else return decode_tile(P, tile, tiles_m, BN);
+  };
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -521,7 +611,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 8);  // one arrive per epilogue warp
+      mbar_init(&tempty_bar[a], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair, on the leader)
       mbar_init(&pfull_bar[a], 1);
       mbar_init(&pempty_bar[a], 1);
     }
@@ -533,13 +623,21 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       tma_prefetch_desc(&map_b);
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (CG == 2) {  // collective over the pair: the same warp of both CTAs, same destination offset
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrive / TMA signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   // barriers, TMEM and descriptors are ready: from here on global memory written by the previous kernel is read
@@ -551,8 +649,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     {
       int it = 0, pc = 0;
       long long w_prod = 0, t_start = clock64();
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(P, tile, tiles_m, BN);
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const TileCoord t = tile_coord(tile);
         if constexpr (TF3) {
           for (int ki = 0; ki < KI; ++ki, ++it) {
             const int s = it % STAGES;
@@ -612,17 +710,34 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
             if (it >= STAGES) DBG_WAIT(w_prod, &empty_bar[s], ((it / STAGES) - 1) & 1);
             if (elect_one()) {
               const int n = (KI - g0) < G ? (KI - g0) : G;
-              mbar_expect_tx(&full_bar[s], n * Cfg::STAGE_BYTES);
+              if constexpr (CG == 2) {
+                // the leader's barrier collects both CTAs' bytes: own 128 pixels of A + own half (128 channels) of B, each
+                if (crank == 0) mbar_expect_tx(&full_bar[s], 2 * n * Cfg::STAGE_BYTES);
 #pragma unroll
-              for (int j = 0; j < G; ++j) {
-                if (j < n) {
-                  const int ki = g0 + j, tap = ki / P.kchunks, kc = ki - tap * P.kchunks;
-                  const int dh = P.taps[tap].dh + (P.nphases == 4 ? t.py : 0);
-                  const int dw = P.taps[tap].dw + (P.nphases == 4 ? t.px : 0);
-                  tma_load_5d(smem_a + (s * G + j) * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, t.w0 + dw, t.h0 + dh, t.b,
-                              P.taps[tap].plane);
-                  tma_load_3d(smem_b + (s * G + j) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0,
-                              t.phase * P.ntaps + tap + (P.w_per_image ? t.b : 0));
+                for (int j = 0; j < G; ++j) {
+                  if (j < n) {
+                    const int ki = g0 + j, tap = ki / P.kchunks, kc = ki - tap * P.kchunks;
+                    const int dh = P.taps[tap].dh + (P.nphases == 4 ? t.py : 0);
+                    const int dw = P.taps[tap].dw + (P.nphases == 4 ? t.px : 0);
+                    tma_load_5d_pair(smem_a + (s * G + j) * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, t.w0 + dw, t.h0 + dh,
+                                     t.b, P.taps[tap].plane);
+                    tma_load_3d_pair(smem_b + (s * G + j) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64,
+                                     t.n0 + crank * (BN / 2), t.phase * P.ntaps + tap);
+                  }
+                }
+              } else {
+                mbar_expect_tx(&full_bar[s], n * Cfg::STAGE_BYTES);
+#pragma unroll
+                for (int j = 0; j < G; ++j) {
+                  if (j < n) {
+                    const int ki = g0 + j, tap = ki / P.kchunks, kc = ki - tap * P.kchunks;
+                    const int dh = P.taps[tap].dh + (P.nphases == 4 ? t.py : 0);
+                    const int dw = P.taps[tap].dw + (P.nphases == 4 ? t.px : 0);
+                    tma_load_5d(smem_a + (s * G + j) * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, t.w0 + dw, t.h0 + dh, t.b,
+                                P.taps[tap].plane);
+                    tma_load_3d(smem_b + (s * G + j) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0,
+                                t.phase * P.ntaps + tap + (P.w_per_image ? t.b : 0));
+                  }
                 }
               }
             }
@@ -635,7 +750,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   } else if (warp == 1) {
     // ================= MMA issuer (whole warp loops; one elected lane issues) =================
     {
-      const uint32_t idesc = TF3 ? make_idesc_tf32(128, BN) : make_idesc_bf16(128, BN);
+      const uint32_t idesc = TF3 ? make_idesc_tf32(128, BN) : make_idesc_bf16(128 * CG, BN);  // pair: M = 256 over both CTAs' lanes
       int it = 0, lt = 0, pc = 0;
       long long w_full = 0, w_tempty = 0, t_start = clock64();
       if constexpr (TF3) {
@@ -643,7 +758,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
         // one of the two TMEM buffers and is handed to the epilogue warps, which sum the segments in fp32 registers with
         // round-to-nearest adds.  Reason (measured, profiles/ + tests/test_gpu_fp32x3.py): the tensor core's accumulator
         // update truncates, so a single TMEM accumulation over n MMAs drifts by ~n * 2^-26 relative - 3e-5 per layer at
-        // K = 13 824 (5 184 MMAs), 70x the error of the fp32 FMA path.  96 MMAs per segment keep it at ~1e-6.
+        // K = 13 824 (5 184 MMAs), 70x the error of the fp32 FMA path.  24 MMAs per segment (TF3_SEG = 2) keep it at the fp32 FMA path's own level;
+        // TF3_SEG = 8 measured 9x that level at nf=64 (2.3e-5 vs 2.6e-6 relative RMS at the last layer).
         int st = 0;  // segments issued by this CTA (TMEM buffer = st & 1)
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
           for (int k0 = 0; k0 < KI; k0 += TF3_SEG, ++st) {
@@ -678,7 +794,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
           }
         }
       }
-      for (int tile = blockIdx.x; tile < num_tiles && !TF3; tile += gridDim.x, ++lt) {
+      for (int tile = tile_first; tile < num_tiles && !TF3 && (CG == 1 || crank == 0); tile += tile_step, ++lt) {  // pair: leader only
         const int acc = lt & 1;
         if (lt >= 2) DBG_WAIT(w_tempty, &tempty_bar[acc], ((lt >> 1) - 1) & 1);  // epilogue drained this buffer
         tc_fence_after();
@@ -739,16 +855,24 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
                   const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + (s * G + j) * A_STAGE_BYTES));
                   const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + (s * G + j) * Cfg::B_STAGE_BYTES));
 #pragma unroll
-                  for (int k = 0; k < 4; ++k)
-                    umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (g0 + j > 0 || k > 0) ? 1u : 0u);
+                  for (int k = 0; k < 4; ++k) {
+                    if constexpr (CG == 2)
+                      umma_bf16_pair(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (g0 + j > 0 || k > 0) ? 1u : 0u);
+                    else
+                      umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (g0 + j > 0 || k > 0) ? 1u : 0u);
+                  }
                 }
               }
-              umma_commit(&empty_bar[s]);
+              if constexpr (CG == 2) umma_commit_pair(&empty_bar[s]);  // frees stage s in both CTAs
+              else umma_commit(&empty_bar[s]);
             }
             __syncwarp();
           }
         }
-        if (elect_one()) umma_commit(&tfull_bar[acc]);
+        if (elect_one()) {
+          if constexpr (CG == 2) umma_commit_pair(&tfull_bar[acc]);  // both epilogues
+          else umma_commit(&tfull_bar[acc]);
+        }
         __syncwarp();
       }
       if (P.dbg && lane == 0) {
@@ -767,12 +891,13 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     const int m = quad * 32 + lane;
     const int trow = P.t_ptr ? *P.t_ptr : 0;
     const bool affine = (P.ss != nullptr) || (P.bias != nullptr) || (P.mult_vec != nullptr);
-    uint8_t* stg = smem_stg + (warp - 2) * 2048;
+    uint8_t* const stg_base = smem_stg + (warp - 2) * 2048 * (Cfg::STG_BUFS > 0 ? Cfg::STG_BUFS : 1);
+    int stg_i = 0;  // staging tile used by the next bulk store (alternates when STG_BUFS == 2)
     long long w_tfull = 0, t_start = clock64();
     int lt = 0, epi_n0 = -1, epi_b = -1;
     int seg_st = 0;  // fp32x3: K segments consumed by this warp (TMEM buffer = seg_st & 1)
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++lt) {
-      const TileCoord t = decode_tile(P, tile, tiles_m, BN);
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++lt) {
+      const TileCoord t = tile_coord(tile);
       const int acc = lt & 1;
       // The per-channel (mult, add) table depends on the N tile (and on the image only with per-image timesteps):
       // rebuild it - two barriers and a dependent global load on the epilogue's critical path - only when that changes.
@@ -780,7 +905,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       if (affine && (t.n0 != epi_n0 || key_b != epi_b)) {
         epi_n0 = t.n0; epi_b = key_b;
         asm volatile("bar.sync 1, 256;" ::: "memory");  // previous tile's reads of s_epi are done
-        const float* ssrow = P.ss ? P.ss + (long long)(trow + t.b * P.ss_img_stride) * P.ss_S + P.ss_off : nullptr;
+        const int tb = (CG == 2 && t.b >= P.B) ? 0 : t.b;  // pair tail: a CTA without pixels still needs a valid table row
+        const float* ssrow = P.ss ? P.ss + (long long)(trow + tb * P.ss_img_stride) * P.ss_S + P.ss_off : nullptr;
         for (int j = et; j < BN; j += 256) {
           const int n = t.n0 + j;
           float mult = 1.f, add = 0.f, bias = 0.f;
@@ -794,7 +920,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
         asm volatile("bar.sync 1, 256;" ::: "memory");
       }
       const int hh = t.h0 + (m >> P.logBW), ww = t.w0 + (m & (P.BW - 1));
-      const bool pvalid = hh < P.H && ww < P.W;
+      const bool pvalid = hh < P.H && ww < P.W && (CG == 1 || t.b < P.B);
       const long long opix = ((long long)t.b * P.Hout + (hh * P.os + t.py)) * P.Wout + (ww * P.os + t.px);
       bf16* orow = P.out + opix * P.out_pitch + t.n0;
       const bf16* rrow = P.res ? P.res + opix * P.res_pitch + t.n0 : nullptr;
@@ -903,7 +1029,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
           // bf16 NHWC through shared memory + TMA store: each lane owns one pixel row of 32 channels (64 B); the
           // staging tile uses the 64B swizzle so the 16-byte st.shared are conflict free and the bulk store writes
           // full, coalesced lines (out-of-range pixels / channels are clipped by TMA).
-          if (lane == 0) bulk_wait_read0();  // the previous bulk store has finished reading the staging tile
+          uint8_t* stg = stg_base + stg_i * 2048;
+          if (lane == 0) {  // the bulk store that last used THIS tile has finished reading it
+            if constexpr (Cfg::STG_BUFS == 2) bulk_wait_read1(); else bulk_wait_read0();
+          }
+          if constexpr (Cfg::STG_BUFS == 2) stg_i ^= 1;
           __syncwarp();
 #pragma unroll
           for (int g = 0; g < 4; ++g)
@@ -974,7 +1104,10 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       // every tcgen05.ld of this warp has completed: hand the accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (CG == 2) mbar_arrive_leader(&tempty_bar[acc]);  // the leader's MMA warp owns both accumulators' reuse
+        else mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if (lane == 0) bulk_wait_all();  // staging smem must stay valid until the last bulk store has read it
     if (P.dbg && threadIdx.x == 64) {
@@ -985,6 +1118,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CG == 2) {
+    cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM: nobody leaves early
+    if (warp == 0)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    return;
+  }
   if (warp == 0) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
@@ -995,6 +1134,9 @@ bool g_persist = true;
 bool g_tma_store = true;
 bool g_rows = true;
 bool g_patch = false;  // opt-in (IRSDE_TC_PATCH=1): measured slower than per-tap boxes, see DESIGN.md
+bool g_pair = true;    // cta_group::2 tiles (CTA pairs, M = 256) for the per-tap BN = 256 3x3 layers; IRSDE_TC_PAIR=0 disables.
+                       // Same-box ABAB (round 2, config 2): 720.0 / 719.5 -> 710.4 / 710.5 ms per chain; the Cout >= 256 3x3
+                       // layers go from 1.18-1.30 to 1.23-1.36 PFLOP/s (84-93 % of the sustained bf16 peak)
 
 }  // namespace
 
@@ -1007,6 +1149,8 @@ struct TcConvDesc {
   int tiles_m, num_tiles;
   bool patch;
   int mode;  // 0 per-tap boxes, 1 PATCH (halo patch, shifted descriptors), 2 ROWS (row-window reuse)
+  bool pair = false;   // CTA-pair (cta_group::2) variant
+  int pair_tiles = 0;  // ceil(tiles_m / 2) * N tiles
 };
 
 bool tc_init(std::string* err) {
@@ -1049,6 +1193,10 @@ bool tc_init(std::string* err) {
     g_rows = !(e && e[0] == '0');
     e = getenv("IRSDE_TC_PATCH");
     g_patch = (e && e[0] == '1');
+    e = getenv("IRSDE_TC_PAIR");
+    g_pair = !(e && e[0] == '0');
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0, 2>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
     e = getenv("IRSDE_PDL");
     g_pdl = (e && e[0] == '1');  // opt-in: measured 0.7 % (UNet step) to 3 % (NAFNet step) slower than plain graph edges
   }
@@ -1127,6 +1275,11 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
     const int tm = P.tilesW * P.tilesH * B * nphases;
     while (BN > 64 && Cout % (BN / 2) == 0 && (long long)tm * ((Cout + BN - 1) / BN) < 74) BN >>= 1;
   }
+  // CTA-pair variant: per-tap mode, full 256-channel N tiles, plain bf16 NHWC output through TMA stores
+  // (not the stride-2 space-to-depth layers: 16 taps over 4 planes measured 10 % slower as pairs)
+  d->pair = g_pair && g_persist && g_tma_store && !patch && !rows && BN == 256 && Cout % 256 == 0 && !P.qsm && !P.w_per_image &&
+            !nchw_out && planes == 1 && ntaps > 1;
+  d->pair_tiles = ((P.tilesW * P.tilesH * B * nphases + 1) / 2) * (Cout / 256);
   d->BN = BN;
   d->grid = dim3((unsigned)(P.tilesW * P.tilesH * B * nphases), (unsigned)((Cout + BN - 1) / BN));
   d->tiles_m = P.tilesW * P.tilesH * B * nphases;
@@ -1170,7 +1323,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   {
     cuuint64_t dims[3] = {(cuuint64_t)Cin, (cuuint64_t)Cout_w, (cuuint64_t)(P.w_per_image ? B : nphases * ntaps)};
     cuuint64_t strides[2] = {(cuuint64_t)Cin * 2, (cuuint64_t)Cout_w * Cin * 2};
-    cuuint32_t box[3] = {64, (cuuint32_t)BN, 1};
+    cuuint32_t box[3] = {64, (cuuint32_t)(d->pair ? BN / 2 : BN), 1};  // pair: each CTA loads its half of the channels
     cuuint32_t es[3] = {1, 1, 1};
     CUresult r = g_encode(&d->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)wpacked, dims, strides, box, es,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1322,6 +1475,25 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
       cudaMemsetAsync(dbg_dev, 0, 256 * 8 * sizeof(unsigned long long), st);
     }
     d->P.dbg = dbg ? dbg_dev : nullptr;
+    if (d->pair) {
+      const int ncl = d->pair_tiles < g_num_sms / 2 ? d->pair_tiles : g_num_sms / 2;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof cfg);
+      cfg.gridDim = dim3(2 * ncl);
+      cfg.blockDim = dim3(320);
+      cfg.dynamicSmemBytes = TcCfgP<256, 0, 2>::SMEM_BYTES;
+      cfg.stream = st;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_persist_kernel<256, 0, 2>, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m,
+                                          d->pair_tiles);
+      return le == cudaSuccess ? 1 : -1;
+    }
 #define TC_LAUNCH(BNV, PV) \
   pdl_launch(conv_tc_persist_kernel<BNV, PV>, g, 320, TcCfgP<BNV, PV>::SMEM_BYTES, st, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles)
     if (d->mode == 3) {
