@@ -20,6 +20,8 @@
 #include <stdio.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace irsde {
@@ -49,6 +51,10 @@ struct TcParams {
   float* out_f32;       // MODE 3 (fp32x3): fp32 NHWC output view (channel offset applied), pitch = out_pitch
   const float* res_f32; // MODE 3: fp32 residual view
   int lo_plane_off;     // MODE 3: plane offset of the "lo" split of the A tensor ([hi planes][lo planes])
+  // tile decode without integer divisions (they cost ~25 instructions + a MUFU.RCP each, five per tile and warp: on layers
+  // with one k-iteration per tile the kernel was ISSUE-bound on them, ncu r02): q = umulhi(x, mg) with mg = ceil(2^32 / d)
+  unsigned mg_tiles_m, mg_tiles_n, mg_tilesW, mg_tilesH, mg_B, mg_pairs_m;  // 0: divisor is 1 (or fast path not provable): see fdiv
+  int epi_kind;         // EK_* combination the epilogue is specialised for (EK_GENERIC: every feature checked at run time)
   int n_fast;           // tile order: N tiles of one M tile are consecutive (1x1 convs with several N tiles, see tc_conv_create)
   int tiles_n;
   int rows_a_bytes;     // ROWS mode: bytes of one A box ((BH+2) x BW x 128)
@@ -518,17 +524,27 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 struct TileCoord {
   int b, phase, py, px, h0, w0, n0;
 };
+// x / d for 0 <= x with x * d < 2^32 (host-checked in tc_fill_magic; mg == 0 selects the plain division)
+__device__ __forceinline__ int fdiv(int x, int d, unsigned mg) { return mg ? (int)__umulhi((unsigned)x, mg) : x / d; }
+enum { EK_QSM = 1, EK_AFF = 2, EK_SILU = 4, EK_RES = 8, EK_GENERIC = 16 };
+
+__device__ __forceinline__ void decode_m(const TcParams& P, int m_idx, TileCoord& t) {
+  int q = fdiv(m_idx, P.tilesW, P.mg_tilesW);
+  const int tw_i = m_idx - q * P.tilesW; m_idx = q;
+  q = fdiv(m_idx, P.tilesH, P.mg_tilesH);
+  const int th_i = m_idx - q * P.tilesH; m_idx = q;
+  q = fdiv(m_idx, P.B, P.mg_B);
+  t.b = m_idx - q * P.B;
+  t.phase = q;
+  t.py = t.phase >> 1; t.px = t.phase & 1;
+  t.h0 = th_i * P.BH; t.w0 = tw_i * P.BW;
+}
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, int tiles_m, int BN) {
   TileCoord t;
   int m_idx;
-  if (P.n_fast) { m_idx = tile / P.tiles_n; t.n0 = (tile - m_idx * P.tiles_n) * BN; }
-  else { m_idx = tile % tiles_m; t.n0 = (tile / tiles_m) * BN; }
-  const int tw_i = m_idx % P.tilesW; m_idx /= P.tilesW;
-  const int th_i = m_idx % P.tilesH; m_idx /= P.tilesH;
-  t.b = m_idx % P.B;
-  t.phase = m_idx / P.B;
-  t.py = t.phase >> 1; t.px = t.phase & 1;
-  t.h0 = th_i * P.BH; t.w0 = tw_i * P.BW;
+  if (P.n_fast) { m_idx = fdiv(tile, P.tiles_n, P.mg_tiles_n); t.n0 = (tile - m_idx * P.tiles_n) * BN; }
+  else { const int q = fdiv(tile, tiles_m, P.mg_tiles_m); m_idx = tile - q * tiles_m; t.n0 = q * BN; }
+  decode_m(P, m_idx, t);
   return t;
 }
 
@@ -537,20 +553,16 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& P, int tile, in
 // TMA stores are clipped).
 __device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& P, int pt, int rank, int tiles_m, int BN) {
   const int pairs_m = (tiles_m + 1) >> 1;
-  const int mp = pt % pairs_m;
-  int m_idx = 2 * mp + rank;
+  const int q = fdiv(pt, pairs_m, P.mg_pairs_m);
+  const int mp = pt - q * pairs_m;
+  const int m_idx = 2 * mp + rank;
   TileCoord t;
-  t.n0 = (pt / pairs_m) * BN;
+  t.n0 = q * BN;
   if (m_idx >= tiles_m) {
     t.b = P.B; t.phase = 0; t.py = 0; t.px = 0; t.h0 = 0; t.w0 = 0;
     return t;
   }
-  const int tw_i = m_idx % P.tilesW; m_idx /= P.tilesW;
-  const int th_i = m_idx % P.tilesH; m_idx /= P.tilesH;
-  t.b = m_idx % P.B;
-  t.phase = m_idx / P.B;
-  t.py = t.phase >> 1; t.px = t.phase & 1;
-  t.h0 = th_i * P.BH; t.w0 = tw_i * P.BW;
+  decode_m(P, m_idx, t);
   return t;
 }
 
@@ -565,7 +577,10 @@ __device__ __forceinline__ TileCoord decode_pair_tile(const TcParams& P, int pt,
     }                                           \
   } while (0)
 
-template <int BN, int MODE, int CG = 1>
+// EKT: EK_* features the epilogue is compiled for.  Only the per-tap BN <= 128 instantiations that serve the 1x1 convs with one
+// or two k-iterations per tile (res_conv: 0, to_qkv: EK_QSM, to_out: EK_AFF) are specialised - there the kernel is issue-bound
+// on epilogue instructions; everything else runs EK_GENERIC (an in-kernel switch over all kinds made ptxas spill 3-4 KB).
+template <int BN, int MODE, int CG = 1, int EKT = 16 /* EK_GENERIC */>
 __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                  const __grid_constant__ CUtensorMap map_b,
                                                                  const __grid_constant__ OutMaps map_o,
@@ -925,7 +940,12 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       bf16* orow = P.out + opix * P.out_pitch + t.n0;
       const bf16* rrow = P.res ? P.res + opix * P.res_pitch + t.n0 : nullptr;
 
-      auto process = [&](uint32_t* v, const int c0) {
+      // KC: std::integral_constant<int, KIND>.  KIND = the EK_* features this conv has, fixed per launch: feature blocks
+      // outside KIND do not exist in the instantiation (the compiler had turned several of them into predicated code that
+      // was issued for every chunk), EK_GENERIC keeps every run-time check (fp32 NCHW output, no-TMA-store fallback).
+      auto process = [&](auto KC, uint32_t* v, const int c0) __attribute__((always_inline)) {
+        constexpr int KIND = decltype(KC)::value;
+        constexpr bool GEN = KIND == EK_GENERIC;
         if constexpr (TF3) {  // fp32 in, fp32 out: IEEE arithmetic, no fast-math approximations
           if (affine) {
 #pragma unroll
@@ -965,7 +985,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
           }
           return;
         }
-        if (P.qsm && t.n0 + c0 < 128) {  // one chunk == one attention head of this pixel's q (module_util.py:168,171)
+        if constexpr (GEN || (KIND & EK_QSM)) if ((!GEN || P.qsm) && t.n0 + c0 < 128) {  // one chunk == one attention head of this pixel's q (module_util.py:168,171)
           float mx = __uint_as_float(v[0]);
 #pragma unroll
           for (int j = 1; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
@@ -980,11 +1000,11 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * inv);
         }
-        if (affine) {
+        if constexpr (GEN || (KIND & EK_AFF)) if (!GEN || affine) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(fmaf(__uint_as_float(v[j]), s_epi[c0 + j], s_epi[BN + c0 + j]));
         }
-        if (P.silu) {
+        if constexpr (GEN || (KIND & EK_SILU)) if (!GEN || P.silu) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             // SiLU(x) = x * (0.5 + 0.5 tanh(x/2)): one MUFU op (tanh.approx, rel. error 2^-11 << bf16 rounding) instead of
@@ -995,7 +1015,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
             v[j] = __float_as_uint(x * fmaf(th, 0.5f, 0.5f));
           }
         }
-        if (P.out_nchw) {
+        if constexpr (GEN) if (P.out_nchw) {
           if (pvalid && hh < P.cropH && ww < P.cropW) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -1012,7 +1032,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
           float f[8];
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = __uint_as_float(v[g * 8 + j]);
-          if (rrow && pvalid && t.n0 + cg < P.Cout) {
+          if constexpr (GEN || (KIND & EK_RES)) if (rrow && pvalid && t.n0 + cg < P.Cout) {
             uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
             const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
 #pragma unroll
@@ -1025,7 +1045,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 #pragma unroll
           for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
         }
-        if (P.tma_store) {
+        if (!GEN || P.tma_store) {
           // bf16 NHWC through shared memory + TMA store: each lane owns one pixel row of 32 channels (64 B); the
           // staging tile uses the 64B swizzle so the 16-byte st.shared are conflict free and the bulk store writes
           // full, coalesced lines (out-of-range pixels / channels are clipped by TMA).
@@ -1051,6 +1071,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
             if (t.n0 + c0 + g * 8 < P.Cout) *reinterpret_cast<uint4*>(orow + c0 + g * 8) = ov[g];
         }
       };
+      typedef std::integral_constant<int, EK_GENERIC> KGen;
 
       constexpr int NCH = (BN / 32 + 1) / 2;  // chunks per warp
       if constexpr (TF3) {
@@ -1082,25 +1103,28 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 #pragma unroll
         for (int i = 0; i < NCH; ++i) {
           const int c0 = (2 * i + half) * 32;
-          if (c0 < BN && t.n0 + c0 < P.Cout) process(reinterpret_cast<uint32_t*>(accf[i]), c0);
+          if (c0 < BN && t.n0 + c0 < P.Cout) process(KGen{}, reinterpret_cast<uint32_t*>(accf[i]), c0);
         }
         continue;
       }
       DBG_WAIT(w_tfull, &tfull_bar[acc], (lt >> 1) & 1);
       tc_fence_after();
       const uint32_t tmem_acc = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN);
-      uint32_t v[2][32];
-      if (half * 32 < BN) tmem_ld32_async(tmem_acc + (uint32_t)(half * 32), v[0]);
+      auto run_chunks = [&](auto KC) __attribute__((always_inline)) {
+        uint32_t v[2][32];
+        if (half * 32 < BN) tmem_ld32_async(tmem_acc + (uint32_t)(half * 32), v[0]);
 #pragma unroll
-      for (int i = 0; i < NCH; ++i) {
-        const int c0 = (2 * i + half) * 32;
-        if (c0 < BN) {
-          tmem_ld_wait(v[i & 1]);
-          const int c1 = (2 * (i + 1) + half) * 32;
-          if (i + 1 < NCH && c1 < BN) tmem_ld32_async(tmem_acc + (uint32_t)c1, v[(i + 1) & 1]);
-          if (t.n0 + c0 < P.Cout) process(v[i & 1], c0);  // chunks entirely past Cout carry no output
+        for (int i = 0; i < NCH; ++i) {
+          const int c0 = (2 * i + half) * 32;
+          if (c0 < BN) {
+            tmem_ld_wait(v[i & 1]);
+            const int c1 = (2 * (i + 1) + half) * 32;
+            if (i + 1 < NCH && c1 < BN) tmem_ld32_async(tmem_acc + (uint32_t)c1, v[(i + 1) & 1]);
+            if (t.n0 + c0 < P.Cout) process(KC, v[i & 1], c0);  // chunks entirely past Cout carry no output
+          }
         }
-      }
+      };
+      run_chunks(std::integral_constant<int, EKT>{});  // EKT: the kernel instantiation's epilogue specialisation (tc_conv_launch)
       // every tcgen05.ld of this warp has completed: hand the accumulator buffer back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -1134,6 +1158,7 @@ bool g_persist = true;
 bool g_tma_store = true;
 bool g_rows = true;
 bool g_patch = false;  // opt-in (IRSDE_TC_PATCH=1): measured slower than per-tap boxes, see DESIGN.md
+int g_epi_spec = 2;  // specialised epilogues: 1 = the per-tap 1x1 layers, 2 = + the ROWS 3x3 ResBlock convs; IRSDE_TC_EPI_SPEC=0: generic only
 bool g_pair = true;    // cta_group::2 tiles (CTA pairs, M = 256) for the per-tap BN = 256 3x3 layers; IRSDE_TC_PAIR=0 disables.
                        // Same-box ABAB (round 2, config 2): 720.0 / 719.5 -> 710.4 / 710.5 ms per chain; the Cout >= 256 3x3
                        // layers go from 1.18-1.30 to 1.23-1.36 PFLOP/s (84-93 % of the sustained bf16 peak)
@@ -1178,6 +1203,15 @@ bool tc_init(std::string* err) {
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 2>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 1>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 2, 1, EK_AFF | EK_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 2>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 2, 1, EK_SILU | EK_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 2>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 2, 1, EK_AFF | EK_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 2>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 2, 1, EK_SILU | EK_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 2>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 0, 1, EK_AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0, 1, EK_AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
+  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0, 1, EK_QSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 3>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 3>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 3>::SMEM_BYTES);
@@ -1195,6 +1229,8 @@ bool tc_init(std::string* err) {
     g_patch = (e && e[0] == '1');
     e = getenv("IRSDE_TC_PAIR");
     g_pair = !(e && e[0] == '0');
+    e = getenv("IRSDE_TC_EPI_SPEC");
+    if (e && e[0] >= '0' && e[0] <= '2') g_epi_spec = e[0] - '0';
     cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0, 2>::SMEM_BYTES);
     cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
     e = getenv("IRSDE_PDL");
@@ -1207,6 +1243,31 @@ bool tc_init(std::string* err) {
     return false;
   }
   return true;
+}
+
+// tile-decode multipliers and the epilogue specialisation of a finished descriptor (called at the end of both creators)
+static void tc_fill_magic(TcConvDesc* d) {
+  TcParams& P = d->P;
+  const unsigned long long max_x = (unsigned long long)d->num_tiles + 2;
+  auto mg = [&](int dv) -> unsigned {
+    if (dv <= 1) return 0u;                                       // x / 1: fdiv falls back to the (free) plain division
+    if (max_x * (unsigned long long)dv >= (1ull << 32)) return 0u;  // exactness not provable: plain division
+    return (unsigned)(((1ull << 32) + (unsigned)dv - 1) / (unsigned)dv);
+  };
+  P.mg_tiles_m = mg(d->tiles_m);
+  P.mg_tiles_n = mg(P.tiles_n);
+  P.mg_tilesW = mg(P.tilesW);
+  P.mg_tilesH = mg(P.tilesH);
+  P.mg_B = mg(P.B);
+  P.mg_pairs_m = mg((d->tiles_m + 1) >> 1);
+  int k = 0;
+  if (P.qsm) k |= EK_QSM;
+  if (P.ss || P.bias || P.mult_vec) k |= EK_AFF;
+  if (P.silu) k |= EK_SILU;
+  if (P.res) k |= EK_RES;
+  const bool known = k == 0 || k == EK_QSM || k == EK_AFF || k == EK_SILU || k == (EK_AFF | EK_SILU) || k == (EK_AFF | EK_RES) ||
+                     k == (EK_SILU | EK_RES);
+  P.epi_kind = (d->mode != 3 && P.tma_store && P.out && known) ? k : EK_GENERIC;
 }
 
 TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win, int Cin, int planes,
@@ -1356,6 +1417,7 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
     }
     P.tma_store = ok ? 1 : 0;
   }
+  tc_fill_magic(d);
   return d;
 }
 
@@ -1445,6 +1507,7 @@ TcConvDesc* tc_conv_create_f32x3(const float* in_split, int B, int Hin, int Win,
   }
   memset(&d->map_o, 0, sizeof d->map_o);
   P.tma_store = 0;
+  tc_fill_magic(d);
   return d;
 }
 
@@ -1462,6 +1525,10 @@ void tc_conv_set_runtime(TcConvDesc* d, const float* ss, const int* t_ptr, int s
   d->P.ss = ss;
   d->P.t_ptr = t_ptr;
   d->P.ss_img_stride = ss_img_stride;
+  if (ss && d->P.epi_kind != EK_GENERIC && !(d->P.epi_kind & EK_AFF)) {  // the time-modulation table arrives at launch time
+    const int k = d->P.epi_kind | EK_AFF;
+    d->P.epi_kind = (k == EK_AFF || k == (EK_AFF | EK_SILU) || k == (EK_AFF | EK_RES)) ? k : EK_GENERIC;
+  }
 }
 
 int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
@@ -1503,11 +1570,23 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
         default: TC_LAUNCH(128, 3); break;
       }
     } else if (d->mode == 2) {
+#define TC_LAUNCH_EK2(BNV, EKV) \
+  pdl_launch(conv_tc_persist_kernel<BNV, 2, 1, EKV>, g, 320, TcCfgP<BNV, 2>::SMEM_BYTES, st, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles)
+      const int ek2 = g_epi_spec >= 2 ? d->P.epi_kind : EK_GENERIC;
       switch (d->BN) {
         case 32: TC_LAUNCH(32, 2); break;
-        case 64: TC_LAUNCH(64, 2); break;
-        default: TC_LAUNCH(128, 2); break;
+        case 64:
+          if (ek2 == (EK_AFF | EK_SILU)) TC_LAUNCH_EK2(64, EK_AFF | EK_SILU);
+          else if (ek2 == (EK_SILU | EK_RES)) TC_LAUNCH_EK2(64, EK_SILU | EK_RES);
+          else TC_LAUNCH(64, 2);
+          break;
+        default:
+          if (ek2 == (EK_AFF | EK_SILU)) TC_LAUNCH_EK2(128, EK_AFF | EK_SILU);
+          else if (ek2 == (EK_SILU | EK_RES)) TC_LAUNCH_EK2(128, EK_SILU | EK_RES);
+          else TC_LAUNCH(128, 2);
+          break;
       }
+#undef TC_LAUNCH_EK2
     } else if (d->mode == 1) {
       switch (d->BN) {
         case 32: TC_LAUNCH(32, 1); break;
@@ -1516,12 +1595,25 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
         default: TC_LAUNCH(256, 1); break;
       }
     } else {
+#define TC_LAUNCH_EK(BNV, EKV) \
+  pdl_launch(conv_tc_persist_kernel<BNV, 0, 1, EKV>, g, 320, TcCfgP<BNV, 0>::SMEM_BYTES, st, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles)
+      const int ek = g_epi_spec >= 1 ? d->P.epi_kind : EK_GENERIC;
       switch (d->BN) {
         case 32: TC_LAUNCH(32, 0); break;
-        case 64: TC_LAUNCH(64, 0); break;
-        case 128: TC_LAUNCH(128, 0); break;
+        case 64:
+          if (ek == 0) TC_LAUNCH_EK(64, 0);
+          else if (ek == EK_AFF) TC_LAUNCH_EK(64, EK_AFF);
+          else TC_LAUNCH(64, 0);
+          break;
+        case 128:
+          if (ek == 0) TC_LAUNCH_EK(128, 0);
+          else if (ek == EK_AFF) TC_LAUNCH_EK(128, EK_AFF);
+          else if (ek == EK_QSM) TC_LAUNCH_EK(128, EK_QSM);
+          else TC_LAUNCH(128, 0);
+          break;
         default: TC_LAUNCH(256, 0); break;
       }
+#undef TC_LAUNCH_EK
     }
 #undef TC_LAUNCH
     if (dbg) {

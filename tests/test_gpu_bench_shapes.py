@@ -115,11 +115,13 @@ def test_conv_tcgen05_multi_tile_vs_torch(lib, scratch_ctx, case):
     assert err.max().item() <= atol, (name, err.max().item(), scale)
 
 
-def test_to_qkv_qsoftmax_epilogue_vs_torch(lib, scratch_ctx):
-    """LinearAttention's to_qkv at the 32^2 level: 1x1 1024->384 whose epilogue applies softmax_d(q) * 32^-0.5 per head
-    (module_util.py:165-171) to output channels < 128."""
+@pytest.mark.parametrize("B,Cin,H,W", [(16, 1024, 32, 32), (1, 128, 256, 256), (2, 64, 256, 256), (3, 128, 128, 128)],
+                         ids=["32^2 C=1024", "256^2 C=128 (N-fastest tile order)", "256^2 C=64 (N-fastest)", "128^2 C=128"])
+def test_to_qkv_qsoftmax_epilogue_vs_torch(lib, scratch_ctx, B, Cin, H, W):
+    """LinearAttention's to_qkv: 1x1 C->384 whose epilogue applies softmax_d(q) * 32^-0.5 per head (module_util.py:165-171)
+    to output channels < 128 - at the 32^2 level and at the 256^2 / 128^2 levels, where the input is larger than L2 and the
+    three N tiles of one pixel tile are processed back to back (N-fastest tile order, conv_tc.cu tc_conv_create)."""
     dev = _dev()
-    B, Cin, H, W = 16, 1024, 32, 32
     assert _tiles(B, H, W, 384) >= 2 * NUM_SMS
     g = torch.Generator(device=dev).manual_seed(7)
     x = torch.randn(B, Cin, H, W, generator=g, device=dev).bfloat16().float()
@@ -134,11 +136,13 @@ def test_to_qkv_qsoftmax_epilogue_vs_torch(lib, scratch_ctx):
     assert (y[:, :128].reshape(B, 4, 32, H, W).sum(2) - 32 ** -0.5).abs().max().item() < 2e-2  # each head sums to 32^-.5 (bf16 terms)
 
 
-def test_to_out_per_image_weights_vs_torch(lib, scratch_ctx):
+@pytest.mark.parametrize("B,H,W,Cout", [(2, 256, 256, 64), (3, 256, 256, 128), (5, 128, 128, 256)],
+                         ids=["256^2 Cout=64", "256^2 Cout=128, 3 images", "128^2 Cout=256"])
+def test_to_out_per_image_weights_vs_torch(lib, scratch_ctx, B, H, W, Cout):
     """The re-associated second einsum + to_out of LinearAttention (module_util.py:176-178): ONE 1x1 GEMM whose [Cout,128]
-    matrix differs per image, at N = 256*256 pixels per image."""
+    matrix differs per image (third TMA coordinate of the weight tensor = image index)."""
     dev = _dev()
-    B, Cin, H, W, Cout = 2, 128, 256, 256, 64
+    Cin = 128
     assert _tiles(B, H, W, Cout) >= 2 * NUM_SMS
     g = torch.Generator(device=dev).manual_seed(11)
     x = torch.randn(B, Cin, H, W, generator=g, device=dev).bfloat16().float()
@@ -150,6 +154,7 @@ def test_to_out_per_image_weights_vs_torch(lib, scratch_ctx):
     err = (y - ref).abs() - 2 ** -8 * ref.abs()
     assert err.max().item() <= 1e-3 * scale, (err.max().item(), scale)
     assert not torch.allclose(y[0], (torch.einsum("oc,chw->ohw", w[1].bfloat16().float(), x[0]) + b[:, None, None]), atol=0.1)
+    assert torch.isfinite(y).all()
 
 
 # ------------------------------------------------------------------------------------------------------------------
