@@ -11,11 +11,13 @@
 // This one kernel serves: 3x3 (9 taps), 1x1 (1 tap), 4x4/s2 (16 taps over 4 space-to-depth planes),
 // nearest-x2-upsample + 3x3 (4 output phases x 4 taps with pre-summed weights).
 //
-// Warp roles (192 threads): warp 0 = TMEM alloc + TMA producer, warp 1 = MMA issuer (one elected
-// lane), warps 2..5 = epilogue (tcgen05.ld -> bias / (scale+1)*x+shift / SiLU / +residual -> bf16 ->
-// 16-byte global stores at the channel offset of the destination concat buffer).
-// Pipeline: STAGES-deep smem ring with full/empty mbarriers; tcgen05.commit releases slots.
-// Two CTAs are co-resident per SM for BN<=128 so one CTA's epilogue overlaps the other's main loop.
+// One persistent kernel (conv_tc_persist_kernel<BN, MODE, CG, EKT>), 320 threads: warp 0 = TMEM alloc + TMA producer, warp 1 =
+// MMA issuer (one elected lane), warps 2..9 = epilogue (tcgen05.ld -> bias / (scale+1)*x+shift / SiLU / q-softmax /
+// +residual -> bf16 -> swizzled staging -> TMA bulk store at the channel offset of the destination concat buffer).
+// Pipeline: STAGES-deep smem ring with full/empty mbarriers (tcgen05.commit releases slots), double-buffered TMEM
+// accumulators so the epilogue of tile i overlaps the main loop of tile i+1.  Variants: MODE 0 per-tap boxes, MODE 2 ROWS
+// (3x3, row-window reuse), MODE 3 fp32x3 (3 x kind::tf32 on split fp32 operands), CG = 2 CTA pairs (cta_group::2), EKT =
+// epilogue features compiled in.
 #include <cuda.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -250,203 +252,12 @@ __device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
 
 constexpr int A_STAGE_BYTES = 128 * 128;  // 128 pixel rows x 64 bf16
 
-template <int BN>
-struct TcCfg {
-  static constexpr int STAGES = (BN == 128) ? 3 : 4;
-  static constexpr int B_STAGE_BYTES = BN * 128;
-  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;
-  static constexpr int EPI_FLOATS = 3 * BN;  // mult, add, bias
-  static constexpr int SMEM_BYTES = 1024 /*align slack*/ + STAGES * STAGE_BYTES + EPI_FLOATS * 4 + 256 /*barriers*/;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
-};
-
-template <int BN>
-__global__ void __launch_bounds__(192) conv_tc_kernel(const __grid_constant__ CUtensorMap map_a,
-                                                      const __grid_constant__ CUtensorMap map_b,
-                                                      const __grid_constant__ TcParams P) {
-  using Cfg = TcCfg<BN>;
-  constexpr int STAGES = Cfg::STAGES;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
-  float* s_epi = reinterpret_cast<float*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_epi + Cfg::EPI_FLOATS);
-  uint64_t* full_bar = bars;
-  uint64_t* empty_bar = bars + STAGES;
-  uint64_t* accum_bar = bars + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 1);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  // ---- tile coordinates
-  int bx = blockIdx.x;
-  const int tw_i = bx % P.tilesW; bx /= P.tilesW;
-  const int th_i = bx % P.tilesH; bx /= P.tilesH;
-  const int b = bx % P.B;
-  const int phase = bx / P.B;
-  const int py = phase >> 1, px = phase & 1;
-  const int h0 = th_i * P.BH, w0 = tw_i * P.BW;
-  const int n0 = blockIdx.y * BN;
-  const int KI = P.ntaps * P.kchunks;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    mbar_init(accum_bar, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    if (lane == 0) {
-      tma_prefetch_desc(&map_a);
-      tma_prefetch_desc(&map_b);
-    }
-    __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "n"(Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  if (warp == 0) {
-    // ================= TMA producer =================
-    if (lane == 0) {
-      int it = 0;
-      for (int tap = 0; tap < P.ntaps; ++tap) {
-        const int dh = P.taps[tap].dh + (P.nphases == 4 ? py : 0);
-        const int dw = P.taps[tap].dw + (P.nphases == 4 ? px : 0);
-        const int plane = P.taps[tap].plane;
-        for (int kc = 0; kc < P.kchunks; ++kc, ++it) {
-          const int s = it % STAGES;
-          if (it >= STAGES) mbar_wait(&empty_bar[s], ((it / STAGES) - 1) & 1);
-          mbar_expect_tx(&full_bar[s], Cfg::STAGE_BYTES);
-          tma_load_5d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kc * 64, w0 + dw, h0 + dh, b, plane);
-          tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, n0, phase * P.ntaps + tap);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BN);
-      for (int it = 0; it < KI; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&full_bar[s], (it / STAGES) & 1);
-        tc_fence_after();
-        const uint64_t adesc = make_sw128_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
-        const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
-#pragma unroll
-        for (int k = 0; k < 4; ++k)  // 4 x (K=16) per 64-channel chunk: +32 B inside the swizzle atom
-          umma_bf16(tmem_base, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
-      }
-      umma_commit(accum_bar);        // accumulator complete
-    }
-  } else {
-    // ================= epilogue (warps 2..5) =================
-    const int et = threadIdx.x - 64;  // 0..127
-    {
-      const int trow = P.t_ptr ? *P.t_ptr : 0;
-      const float* ssrow = P.ss ? P.ss + (long long)(trow + b * P.ss_img_stride) * P.ss_S + P.ss_off : nullptr;
-      for (int j = et; j < BN; j += 128) {
-        const int n = n0 + j;
-        float mult = 1.f, add = 0.f, bias = 0.f;
-        if (n < P.Cout) {
-          if (ssrow) { mult = ssrow[n] + 1.0f; add = ssrow[P.Cout + n]; }
-          if (P.bias) bias = P.bias[n];
-        }
-        s_epi[j] = mult; s_epi[BN + j] = add; s_epi[2 * BN + j] = bias;
-      }
-      asm volatile("bar.sync 1, 128;" ::: "memory");  // epilogue warps only
-    }
-    const int quad = warp & 3;            // TMEM lane quadrant this warp may read
-    const int m = quad * 32 + lane;       // accumulator row == pixel index inside the tile
-    const int hh = h0 + (m >> P.logBW), ww = w0 + (m & (P.BW - 1));
-    const bool pvalid = hh < P.H && ww < P.W;
-    const long long opix = ((long long)b * P.Hout + (hh * P.os + py)) * P.Wout + (ww * P.os + px);
-    bf16* orow = P.out + opix * P.out_pitch + n0;
-    const bf16* rrow = P.res ? P.res + opix * P.res_pitch + n0 : nullptr;
-    mbar_wait(accum_bar, 0);
-    tc_fence_after();
-#pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)c0, v);
-      if (pvalid && P.out_nchw) {
-        if (hh < P.cropH && ww < P.cropW) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = n0 + c0 + j;
-            if (n < P.Cout) {
-              float x = __uint_as_float(v[j]);
-              x = (x + s_epi[2 * BN + c0 + j]) * s_epi[c0 + j] + s_epi[BN + c0 + j];
-              if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
-              P.out_nchw[(((long long)b * P.Cout + n) * P.cropH + hh) * P.cropW + ww] = x;
-            }
-          }
-        }
-      } else if (pvalid) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {  // groups of 8 channels = one 16-byte store
-          const int cg = c0 + g * 8;
-          if (n0 + cg < P.Cout) {
-            float f[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float x = __uint_as_float(v[g * 8 + j]);
-              x = (x + s_epi[2 * BN + cg + j]) * s_epi[cg + j] + s_epi[BN + cg + j];
-              if (P.silu) x = __fdividef(x, 1.0f + __expf(-x));
-              f[j] = x;
-            }
-            if (rrow) {
-              uint4 r = *reinterpret_cast<const uint4*>(rrow + cg);
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&r);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                f[2 * j] += __low2float(r2[j]);
-                f[2 * j + 1] += __high2float(r2[j]);
-              }
-            }
-            uint4 o;
-            __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o2[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-            *reinterpret_cast<uint4*>(orow + cg) = o;
-          }
-        }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
-  }
-}
-
 // =====================================================================================================
-// Persistent variant (default): one CTA per SM loops over output tiles.  The TMEM accumulator is
+// Persistent kernel: one CTA per SM loops over output tiles.  The TMEM accumulator is
 // double buffered (2 x BN columns) so the epilogue of tile i overlaps the MMA main loop of tile i+1,
 // the smem ring is as deep as 192 KB allows (BN=256: 4, BN=128: 6, BN<=64: 8 stages) to cover TMA
 // latency, and the prologue (barrier init, TMEM alloc, descriptor prefetch) is paid once per SM.
 // =====================================================================================================
-//
-// PATCH mode (3x3 stride-1 convs): the tile is 8 x 16 pixels and, per 64-channel chunk, ONE TMA box of the
-// (8+2) x (16+2) halo patch is loaded and reused by all 9 taps: tap (dh,dw) is the same shared-memory patch
-// addressed through a UMMA descriptor whose start is shifted by ((dh+1)*10 + (dw+1)) pixel rows (128 B each)
-// and whose 8-row-group stride (SBO) is the patch row pitch (10 * 128 B).  The 128B swizzle is a function of
-// the shared-memory address, so TMA's write pattern and the shifted UMMA reads agree.  A-operand L2->smem
-// traffic drops from 9 x 16 KB to 22.5 KB per chunk; only the weight tiles stream through the ring.
-constexpr int PATCH_W = 10, PATCH_H = 18;
-constexpr int PATCH_BYTES = PATCH_W * PATCH_H * 128;   // 23040
-constexpr int PATCH_STRIDE = 24 * 1024;                // per-buffer stride (1024-aligned)
-
 //
 // ROWS mode (default for 3x3 stride-1 convs with BN <= 128): a stage is ONE TMA box of (BH+2) image rows x BW pixels
 // for a given horizontal shift dw, plus the three weight tiles of the taps (dh=-1,0,1; dw).  The three vertical taps
@@ -466,11 +277,10 @@ constexpr int ROWS_A_SLOT = 20 * 1024;  // (8+2) rows x 16 px x 128 B (or 18 x 8
 // and SM: the BN = 256 layers were L2->smem feed bound, MMA warp ~40 % of the time on the `full` barrier).
 template <int BN, int MODE, int CG = 1>
 struct TcCfgP {
-  static constexpr bool PATCH = MODE == 1;
   static constexpr bool ROWS = MODE == 2;
   static constexpr bool TF3 = MODE == 3;
   static constexpr int B_STAGE_BYTES = BN * 128 / CG;
-  // non-PATCH: G consecutive k-iterations (64-channel chunks) share one full/empty barrier round, which amortises the
+  // G consecutive k-iterations (64-channel chunks) share one full/empty barrier round, which amortises the
   // mbarrier wait + tcgen05.commit of the single MMA-issuing thread over 4*G MMAs (matters for narrow N tiles)
   static constexpr int G = 1;  // measured: G=2 trades issue overhead for coarser prefetch granularity; no net gain
   // Epilogue staging for the TMA stores: one 2 KB tile per epilogue warp.  (Two tiles per warp - so that a warp need not
@@ -480,11 +290,11 @@ struct TcCfgP {
   static constexpr int STG_BUFS = TF3 ? 0 : 1;
   static constexpr int STAGES = CG == 2 ? 6 : TF3 ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
                                 : ROWS ? (BN == 128 ? 3 : (BN == 64 ? 4 : 5))
-                                       : (PATCH ? (BN == 256 ? 4 : (BN == 128 ? 8 : 12)) : (BN == 256 ? 4 : (BN == 128 ? 6 : 8)));
+                                       : (BN == 256 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int BSUB = ROWS ? 3 : (TF3 ? 2 : 1);  // weight tiles per stage
-  static constexpr int STAGE_BYTES = PATCH ? B_STAGE_BYTES : A_STAGE_BYTES + B_STAGE_BYTES;  // per k-iteration (modes 0/1)
+  static constexpr int STAGE_BYTES = A_STAGE_BYTES + B_STAGE_BYTES;  // per k-iteration (mode 0)
   static constexpr int A_BYTES = TF3 ? STAGES * 2 * A_STAGE_BYTES
-                                     : (ROWS ? STAGES * ROWS_A_SLOT : (PATCH ? 2 * PATCH_STRIDE : STAGES * G * A_STAGE_BYTES));
+                                     : (ROWS ? STAGES * ROWS_A_SLOT : STAGES * G * A_STAGE_BYTES);
   static constexpr int EPI_FLOATS = 3 * BN;
   static constexpr int STG_BYTES = STG_BUFS * 8 * 2048;  // per epilogue warp: STG_BUFS 32 rows x 64 B staging tiles for TMA stores
   static constexpr int SMEM_BYTES = 1024 + A_BYTES + STAGES * G * BSUB * B_STAGE_BYTES + STG_BYTES + EPI_FLOATS * 4 + 512;
@@ -587,7 +397,6 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
                                                                  const __grid_constant__ TcParams P, int tiles_m,
                                                                  int num_tiles) {
   using Cfg = TcCfgP<BN, MODE, CG>;
-  constexpr bool PATCH = Cfg::PATCH;
   constexpr bool ROWS = Cfg::ROWS;
   constexpr bool TF3 = Cfg::TF3;
   constexpr int STAGES = Cfg::STAGES;
@@ -595,7 +404,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   pdl_trigger();  // the next kernel may be scheduled; this one's prologue below touches no global memory
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* smem_a = smem;                       // A ring, or the two halo-patch buffers in PATCH mode
+  uint8_t* smem_a = smem;                       // A ring
   uint8_t* smem_b = smem + Cfg::A_BYTES;
   uint8_t* smem_stg = smem_b + STAGES * Cfg::G * Cfg::BSUB * Cfg::B_STAGE_BYTES;  // 1024-aligned
   float* s_epi = reinterpret_cast<float*>(smem_stg + Cfg::STG_BYTES);
@@ -604,8 +413,6 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   uint64_t* empty_bar = bars + STAGES;
   uint64_t* tfull_bar = bars + 2 * STAGES;       // [2] accumulator ready
   uint64_t* tempty_bar = bars + 2 * STAGES + 2;  // [2] accumulator drained
-  uint64_t* pfull_bar = bars + 2 * STAGES + 4;   // [2] halo patch landed (PATCH)
-  uint64_t* pempty_bar = bars + 2 * STAGES + 6;  // [2] halo patch consumed (PATCH)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * STAGES + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -627,8 +434,6 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
       mbar_init(&tempty_bar[a], 8 * CG);  // one arrive per epilogue warp (of both CTAs of a pair, on the leader)
-      mbar_init(&pfull_bar[a], 1);
-      mbar_init(&pempty_bar[a], 1);
     }
     fence_barrier_init();
   }
@@ -662,7 +467,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
   if (warp == 0) {
     // ================= TMA producer (whole warp loops; one elected lane issues) =================
     {
-      int it = 0, pc = 0;
+      int it = 0;
       long long w_prod = 0, t_start = clock64();
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const TileCoord t = tile_coord(tile);
@@ -695,25 +500,6 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 #pragma unroll
                 for (int j = 0; j < 3; ++j)  // taps (dh = j-1, dw = dwi-1): index (dh+1)*3 + (dw+1)
                   tma_load_3d(smem_b + (s * 3 + j) * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0, j * 3 + dwi);
-              }
-              __syncwarp();
-            }
-          }
-        } else if constexpr (PATCH) {
-          for (int kc = 0; kc < P.kchunks; ++kc, ++pc) {
-            const int pb = pc & 1;
-            if (pc >= 2) DBG_WAIT(w_prod, &pempty_bar[pb], ((pc >> 1) - 1) & 1);
-            if (elect_one()) {
-              mbar_expect_tx(&pfull_bar[pb], PATCH_BYTES);
-              tma_load_5d(smem_a + pb * PATCH_STRIDE, &map_a, &pfull_bar[pb], kc * 64, t.w0 - 1, t.h0 - 1, t.b, 0);
-            }
-            __syncwarp();
-            for (int tap = 0; tap < 9; ++tap, ++it) {
-              const int s = it % STAGES;
-              if (it >= STAGES) DBG_WAIT(w_prod, &empty_bar[s], ((it / STAGES) - 1) & 1);
-              if (elect_one()) {
-                mbar_expect_tx(&full_bar[s], Cfg::B_STAGE_BYTES);
-                tma_load_3d(smem_b + s * Cfg::B_STAGE_BYTES, &map_b, &full_bar[s], kc * 64, t.n0, tap);
               }
               __syncwarp();
             }
@@ -766,7 +552,7 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     // ================= MMA issuer (whole warp loops; one elected lane issues) =================
     {
       const uint32_t idesc = TF3 ? make_idesc_tf32(128, BN) : make_idesc_bf16(128 * CG, BN);  // pair: M = 256 over both CTAs' lanes
-      int it = 0, lt = 0, pc = 0;
+      int it = 0, lt = 0;
       long long w_full = 0, w_tempty = 0, t_start = clock64();
       if constexpr (TF3) {
         // fp32x3: the K loop of a tile is cut into SEGMENTS of TF3_SEG k-iterations; each segment accumulates from zero in
@@ -833,28 +619,6 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
               umma_commit(&empty_bar[s]);
             }
             __syncwarp();
-          }
-        } else if constexpr (PATCH) {
-          for (int kc = 0; kc < P.kchunks; ++kc, ++pc) {
-            const int pb = pc & 1;
-            DBG_WAIT(w_full, &pfull_bar[pb], (pc >> 1) & 1);
-            const uint32_t patch = smem_u32(smem_a + pb * PATCH_STRIDE);
-            for (int tap = 0; tap < 9; ++tap, ++it) {
-              const int s = it % STAGES;
-              DBG_WAIT(w_full, &full_bar[s], (it / STAGES) & 1);
-              tc_fence_after();
-              if (elect_one()) {
-                const int dh = P.taps[tap].dh, dw = P.taps[tap].dw;
-                const uint64_t adesc = make_sw128_desc(patch + (uint32_t)(((dh + 1) * PATCH_W + dw + 1) * 128), PATCH_W * 128);
-                const uint64_t bdesc = make_sw128_desc(smem_u32(smem_b + s * Cfg::B_STAGE_BYTES));
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                  umma_bf16(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kc > 0 || tap > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&empty_bar[s]);
-                if (tap == 8) umma_commit(&pempty_bar[pb]);  // all 9 taps of this chunk issued
-              }
-              __syncwarp();
-            }
           }
         } else {
           constexpr int G = Cfg::G;
@@ -1154,10 +918,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 }
 
 int g_num_sms = 148;
-bool g_persist = true;
 bool g_tma_store = true;
 bool g_rows = true;
-bool g_patch = false;  // opt-in (IRSDE_TC_PATCH=1): measured slower than per-tap boxes, see DESIGN.md
 int g_epi_spec = 2;  // specialised epilogues: 1 = the per-tap 1x1 layers, 2 = + the ROWS 3x3 ResBlock convs; IRSDE_TC_EPI_SPEC=0: generic only
 bool g_pair = true;    // cta_group::2 tiles (CTA pairs, M = 256) for the per-tap BN = 256 3x3 layers; IRSDE_TC_PAIR=0 disables.
                        // Same-box ABAB (round 2, config 2): 720.0 / 719.5 -> 710.4 / 710.5 ms per chain; the Cout >= 256 3x3
@@ -1172,8 +934,7 @@ struct TcConvDesc {
   int BN;
   dim3 grid;
   int tiles_m, num_tiles;
-  bool patch;
-  int mode;  // 0 per-tap boxes, 1 PATCH (halo patch, shifted descriptors), 2 ROWS (row-window reuse)
+  int mode;  // 0 per-tap boxes, 2 ROWS (row-window reuse), 3 fp32x3
   bool pair = false;   // CTA-pair (cta_group::2) variant
   int pair_tiles = 0;  // ceil(tiles_m / 2) * N tiles
 };
@@ -1188,21 +949,13 @@ bool tc_init(std::string* err) {
     return false;
   }
   g_encode = (EncodeTiledFn)fn;
-  cudaFuncSetAttribute(conv_tc_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<32>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<64>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<128>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfg<256>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<32, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 0>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 1>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 2>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 0>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 1>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 2>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 1>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 2>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<256, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 1>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<64, 2, 1, EK_AFF | EK_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 2>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<64, 2, 1, EK_SILU | EK_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 2>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 2, 1, EK_AFF | EK_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 2>::SMEM_BYTES);
@@ -1219,14 +972,10 @@ bool tc_init(std::string* err) {
     int dev = 0, n = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) g_num_sms = n;
-    const char* e = getenv("IRSDE_TC_PERSIST");
-    g_persist = !(e && e[0] == '0');
-    e = getenv("IRSDE_TC_TMA_STORE");
+    const char* e = getenv("IRSDE_TC_TMA_STORE");
     g_tma_store = !(e && e[0] == '0');
     e = getenv("IRSDE_TC_ROWS");
     g_rows = !(e && e[0] == '0');
-    e = getenv("IRSDE_TC_PATCH");
-    g_patch = (e && e[0] == '1');
     e = getenv("IRSDE_TC_PAIR");
     g_pair = !(e && e[0] == '0');
     e = getenv("IRSDE_TC_EPI_SPEC");
@@ -1300,19 +1049,15 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   P.qsm = (flags & TC_FLAG_QSOFTMAX) ? 1 : 0;
   P.w_per_image = (flags & TC_FLAG_W_PER_IMAGE) ? 1 : 0;
   if (P.w_per_image && (ntaps != 1 || nphases != 1)) return bad("per-image weights need a 1x1 conv");
-  if ((P.qsm || P.w_per_image) && !(g_persist && g_tma_store)) return bad("fused attention epilogues need the persistent TMA-store kernel");
-  // PATCH mode: plain 3x3 / stride 1 / pad 1 on the persistent kernel
-  bool patch = g_persist && g_patch && nphases == 1 && planes == 1 && ntaps == 9;
-  for (int i = 0; patch && i < 9; ++i) patch = taps[i].dh == i / 3 - 1 && taps[i].dw == i % 3 - 1 && taps[i].plane == 0;
+  if ((P.qsm || P.w_per_image) && !g_tma_store) return bad("fused attention epilogues need the TMA-store epilogue");
   int BN = Cout >= 256 ? 256 : (Cout > 64 ? 128 : (Cout > 32 ? 64 : 32));
   if (BN == 256 && Cout % 256 != 0 && Cout % 128 == 0) BN = 128;  // e.g. to_qkv (384): no half-empty N tile
   bool rows = false;
-  if (!patch && g_persist && g_rows && nphases == 1 && planes == 1 && ntaps == 9 && BN <= 128) {
+  if (g_rows && nphases == 1 && planes == 1 && ntaps == 9 && BN <= 128) {
     rows = true;
     for (int i = 0; rows && i < 9; ++i) rows = taps[i].dh == i / 3 - 1 && taps[i].dw == i % 3 - 1 && taps[i].plane == 0;
   }
-  d->patch = patch;
-  d->mode = patch ? 1 : (rows ? 2 : 0);
+  d->mode = rows ? 2 : 0;
   // tile shape: BW x BH = 128 pixels, minimise padded work
   long long best = -1;
   for (int bw = 128; bw >= 8; bw >>= 1) {
@@ -1320,7 +1065,6 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
     long long cost = (long long)((Win + bw - 1) / bw) * bw * ((Hin + bh - 1) / bh) * bh;
     if (best < 0 || cost < best) { best = cost; P.BW = bw; P.BH = bh; }
   }
-  if (patch) { P.BW = 8; P.BH = 16; }
   if (rows) {  // (BH+2) x BW box must fit the 20 KB slot: BW <= 16
     if (Win >= 16) { P.BW = 16; P.BH = 8; } else { P.BW = 8; P.BH = 16; }
     P.rows_a_bytes = (P.BH + 2) * P.BW * 128;
@@ -1332,13 +1076,13 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
   // Small problems (NAFNet's 16x16 levels, sharded deep UNet levels): fewer tiles than half the SMs means a handful
   // of CTAs stream all the weights; narrower N tiles spread that over more SMs.  Tap mode 0 accumulates in the same
   // K order for every BN, so results do not depend on this choice (and hence not on the batch size).
-  if (g_persist && !patch && !rows && !P.qsm && !nchw_out) {
+  if (!rows && !P.qsm && !nchw_out) {
     const int tm = P.tilesW * P.tilesH * B * nphases;
     while (BN > 64 && Cout % (BN / 2) == 0 && (long long)tm * ((Cout + BN - 1) / BN) < 74) BN >>= 1;
   }
   // CTA-pair variant: per-tap mode, full 256-channel N tiles, plain bf16 NHWC output through TMA stores
   // (not the stride-2 space-to-depth layers: 16 taps over 4 planes measured 10 % slower as pairs)
-  d->pair = g_pair && g_persist && g_tma_store && !patch && !rows && BN == 256 && Cout % 256 == 0 && !P.qsm && !P.w_per_image &&
+  d->pair = g_pair && g_tma_store && !rows && BN == 256 && Cout % 256 == 0 && !P.qsm && !P.w_per_image &&
             !nchw_out && planes == 1 && ntaps > 1;
   d->pair_tiles = ((P.tilesW * P.tilesH * B * nphases + 1) / 2) * (Cout / 256);
   d->BN = BN;
@@ -1368,7 +1112,6 @@ TcConvDesc* tc_conv_create(const bf16* in, int in_pitch, int B, int Hin, int Win
       strides[3] = strides[2] * B;
     }
     cuuint32_t box[5] = {64, (cuuint32_t)P.BW, (cuuint32_t)P.BH, 1, 1};
-    if (patch) { box[1] = PATCH_W; box[2] = PATCH_H; }
     if (rows) { box[2] = (cuuint32_t)(P.BH + 2); }
     cuuint32_t es[5] = {1, 1, 1, 1, 1};
     CUresult r = g_encode(&d->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, (void*)in, dims, strides, box, es,
@@ -1431,7 +1174,6 @@ TcConvDesc* tc_conv_create_f32x3(const float* in_split, int B, int Hin, int Win,
     return nullptr;
   };
   if (!g_encode) return bad("tc_init not called");
-  if (!g_persist) return bad("fp32x3 needs the persistent kernel");
   if (ntaps < 1 || ntaps > 16) return bad("ntaps out of range");
   if (planes < 1) return bad("fp32x3: planes must be >= 1");
   const bool nchw_out = (out == nullptr);
@@ -1454,7 +1196,6 @@ TcConvDesc* tc_conv_create_f32x3(const float* in_split, int B, int Hin, int Win,
   P.lo_plane_off = planes;
   for (int i = 0; i < ntaps; ++i) P.taps[i] = taps[i];
   int BN = Cout > 64 ? 128 : (Cout > 32 ? 64 : 32);
-  d->patch = false;
   d->mode = 3;
   long long best = -1;
   for (int bw = 128; bw >= 8; bw >>= 1) {
@@ -1513,7 +1254,7 @@ TcConvDesc* tc_conv_create_f32x3(const float* in_split, int B, int Hin, int Win,
 
 void tc_conv_destroy(TcConvDesc* d) { delete d; }
 
-bool tc_fused_attention_available() { return g_persist && g_tma_store; }
+bool tc_fused_attention_available() { return g_tma_store; }
 
 void tc_conv_set_out_nchw(TcConvDesc* d, float* out, int cropH, int cropW) {
   d->P.out_nchw = out;
@@ -1532,7 +1273,7 @@ void tc_conv_set_runtime(TcConvDesc* d, const float* ss, const int* t_ptr, int s
 }
 
 int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
-  if (g_persist) {
+  {
     const unsigned g = (unsigned)(d->num_tiles < g_num_sms ? d->num_tiles : g_num_sms);
     static unsigned long long* dbg_dev = nullptr;
     const char* dbg_env = getenv("IRSDE_TC_DEBUG");
@@ -1587,13 +1328,6 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
           break;
       }
 #undef TC_LAUNCH_EK2
-    } else if (d->mode == 1) {
-      switch (d->BN) {
-        case 32: TC_LAUNCH(32, 1); break;
-        case 64: TC_LAUNCH(64, 1); break;
-        case 128: TC_LAUNCH(128, 1); break;
-        default: TC_LAUNCH(256, 1); break;
-      }
     } else {
 #define TC_LAUNCH_EK(BNV, EKV) \
   pdl_launch(conv_tc_persist_kernel<BNV, 0, 1, EKV>, g, 320, TcCfgP<BNV, 0>::SMEM_BYTES, st, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->num_tiles)
@@ -1622,18 +1356,11 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
       cudaMemcpy(h, dbg_dev, sizeof h, cudaMemcpyDeviceToHost);
       double a[8] = {0};
       for (unsigned i = 0; i < g; ++i) for (int k = 0; k < 8; ++k) a[k] += (double)h[i * 8 + k] / g;
-      fprintf(stderr, "TCDBG BN=%d patch=%d grid=%u tiles=%d ntaps=%d kch=%d | prod wait %.0f / %.0f | mma wait full %.0f tempty %.0f / %.0f | epi wait tfull %.0f / %.0f (tiles/cta %.1f)\n",
+      fprintf(stderr, "TCDBG BN=%d mode=%d grid=%u tiles=%d ntaps=%d kch=%d | prod wait %.0f / %.0f | mma wait full %.0f tempty %.0f / %.0f | epi wait tfull %.0f / %.0f (tiles/cta %.1f)\n",
               d->BN, d->mode, g, d->num_tiles, d->P.ntaps, d->P.kchunks, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7]);
     }
     return 1;
   }
-  switch (d->BN) {
-    case 32: conv_tc_kernel<32><<<d->grid, 192, TcCfg<32>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
-    case 64: conv_tc_kernel<64><<<d->grid, 192, TcCfg<64>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
-    case 128: conv_tc_kernel<128><<<d->grid, 192, TcCfg<128>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
-    default: conv_tc_kernel<256><<<d->grid, 192, TcCfg<256>::SMEM_BYTES, st>>>(d->map_a, d->map_b, d->P); break;
-  }
-  return 1;
 }
 
 }  // namespace irsde
