@@ -920,7 +920,8 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
 int g_num_sms = 148;
 bool g_tma_store = true;
 bool g_rows = true;
-int g_epi_spec = 2;  // specialised epilogues: 1 = the per-tap 1x1 layers, 2 = + the ROWS 3x3 ResBlock convs; IRSDE_TC_EPI_SPEC=0: generic only
+int g_epi_spec = 3;  // specialised epilogues: 1 = the per-tap 1x1 layers, 2 = + the ROWS 3x3 ResBlock convs, 3 = + the BN = 256
+                     // CTA-pair ResBlock convs and biased per-tap convs; IRSDE_TC_EPI_SPEC=0: generic only
 bool g_pair = true;    // cta_group::2 tiles (CTA pairs, M = 256) for the per-tap BN = 256 3x3 layers; IRSDE_TC_PAIR=0 disables.
                        // Same-box ABAB (round 2, config 2): 720.0 / 719.5 -> 710.4 / 710.5 ms per chain; the Cout >= 256 3x3
                        // layers go from 1.18-1.30 to 1.23-1.36 PFLOP/s (84-93 % of the sustained bf16 peak)
@@ -979,8 +980,14 @@ bool tc_init(std::string* err) {
     e = getenv("IRSDE_TC_PAIR");
     g_pair = !(e && e[0] == '0');
     e = getenv("IRSDE_TC_EPI_SPEC");
-    if (e && e[0] >= '0' && e[0] <= '2') g_epi_spec = e[0] - '0';
+    if (e && e[0] >= '0' && e[0] <= '3') g_epi_spec = e[0] - '0';
     cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0, 2>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2, EK_AFF | EK_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0, 2>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2, EK_SILU | EK_RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0, 2>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 1, EK_AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2, EK_AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0, 2>::SMEM_BYTES);
+    cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<256, 0, 2>::SMEM_BYTES);
     cudaFuncSetAttribute(conv_tc_persist_kernel<256, 0, 2>, cudaFuncAttributeNonPortableClusterSizeAllowed, 0);
     e = getenv("IRSDE_PDL");
     g_pdl = (e && e[0] == '1');  // opt-in: measured 0.7 % (UNet step) to 3 % (NAFNet step) slower than plain graph edges
@@ -1298,8 +1305,18 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
       attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr;
       cfg.numAttrs = 1;
-      cudaError_t le = cudaLaunchKernelEx(&cfg, conv_tc_persist_kernel<256, 0, 2>, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m,
-                                          d->pair_tiles);
+      const int ekp = g_epi_spec >= 3 ? d->P.epi_kind : EK_GENERIC;
+      cudaError_t le;
+      if (ekp == (EK_AFF | EK_SILU))
+        le = cudaLaunchKernelEx(&cfg, conv_tc_persist_kernel<256, 0, 2, EK_AFF | EK_SILU>, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->pair_tiles);
+      else if (ekp == (EK_SILU | EK_RES))
+        le = cudaLaunchKernelEx(&cfg, conv_tc_persist_kernel<256, 0, 2, EK_SILU | EK_RES>, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->pair_tiles);
+      else if (ekp == EK_AFF)
+        le = cudaLaunchKernelEx(&cfg, conv_tc_persist_kernel<256, 0, 2, EK_AFF>, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->pair_tiles);
+      else if (ekp == 0)
+        le = cudaLaunchKernelEx(&cfg, conv_tc_persist_kernel<256, 0, 2, 0>, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->pair_tiles);
+      else
+        le = cudaLaunchKernelEx(&cfg, conv_tc_persist_kernel<256, 0, 2>, d->map_a, d->map_b, d->map_o, d->P, d->tiles_m, d->pair_tiles);
       return le == cudaSuccess ? 1 : -1;
     }
 #define TC_LAUNCH(BNV, PV) \
@@ -1345,7 +1362,11 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
           else if (ek == EK_QSM) TC_LAUNCH_EK(128, EK_QSM);
           else TC_LAUNCH(128, 0);
           break;
-        default: TC_LAUNCH(256, 0); break;
+        default:
+          if (g_epi_spec >= 3 && ek == EK_AFF) TC_LAUNCH_EK(256, EK_AFF);   // downsample convs / deep to_out (bias)
+          else if (g_epi_spec >= 3 && ek == 0) TC_LAUNCH_EK(256, 0);       // deep res_conv
+          else TC_LAUNCH(256, 0);
+          break;
       }
 #undef TC_LAUNCH_EK
     }

@@ -13,8 +13,8 @@ PY
   grep "^PROF" gpurun_out/spec_$1.err > gpurun_out/prof_dump_spec_$1.txt
 }
 NEW=image-restoration-sde_b200/libirsde_b200.so
-run s1 $NEW 1; run s2 $NEW 2; run s1b $NEW 1; run s2b $NEW 2
-python scripts/prof_table.py gpurun_out/prof_dump_spec_s1.txt k3 | grep -E "256x256|128x128|total" | cut -c1-64,70-80 > gpurun_out/spec_gen_k1.txt
-python scripts/prof_table.py gpurun_out/prof_dump_spec_s2.txt k3 | grep -E "256x256|128x128|total" | cut -c70-80 > gpurun_out/spec_spec_k1.txt
-python scripts/prof_table.py gpurun_out/prof_dump_spec_s1b.txt k3 | grep -E "256x256|128x128|total" | cut -c70-80 > gpurun_out/spec_prev_k1.txt
+run s2 $NEW 2; run s3 $NEW 3; run s2b $NEW 2; run s3b $NEW 3
+python scripts/prof_table.py gpurun_out/prof_dump_spec_s2.txt k3 | grep -E "32x32|64x64|total" | cut -c1-64,70-80 > gpurun_out/spec_gen_k1.txt
+python scripts/prof_table.py gpurun_out/prof_dump_spec_s3.txt k3 | grep -E "32x32|64x64|total" | cut -c70-80 > gpurun_out/spec_spec_k1.txt
+python scripts/prof_table.py gpurun_out/prof_dump_spec_s2b.txt k3 | grep -E "32x32|64x64|total" | cut -c70-80 > gpurun_out/spec_prev_k1.txt
 paste -d'|' gpurun_out/spec_gen_k1.txt gpurun_out/spec_spec_k1.txt gpurun_out/spec_prev_k1.txt
