@@ -41,7 +41,7 @@ def main():
     cols = [i for i, h in enumerate(hdr) if h in KEEP or "tensor" in h.lower()]
     body = [r for r in rows[hdr_i + 2:] if len(r) >= len(hdr)]
     kn = hdr.index("Kernel Name")
-    names = [r[kn] for r in body]
+    names = [r[kn].replace("(int)", "") for r in body]   # ncu prints template arguments as "(int)128" in some pages
     for rx in require:
         if not any(re.search(rx, n) for n in names):
             sys.stderr.write("ncu_summarize: no kernel matches required pattern %r (capture is not of the shipped kernel mix)\n" % rx)

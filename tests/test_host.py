@@ -323,3 +323,23 @@ def test_tiled_refusion_gloo(world):
         for k, (y0, y1, x0, x1) in enumerate(boxes):
             ref[b:b + 1, :, y0:y1, x0:x1] = _fake_chain(z[b:b + 1, :, y0:y1, x0:x1], [b * len(boxes) + k])
     assert torch.allclose(single, ae.decode(ref, h), rtol=1e-6, atol=1e-4)   # batch-of-tiles vs one-tile reductions: last ulp
+
+
+def test_ncu_summariser_refuses_a_capture_without_the_shipped_kernels(tmp_path):
+    """scripts/ncu_summarize.py --require: the round-1 profiles described a kernel that was no longer the shipped one; the
+    summariser now fails (exit 3) unless every required kernel-name pattern occurs, and records the kernel mix."""
+    import json
+    import subprocess
+    import sys
+    raw = tmp_path / "raw.csv"
+    raw.write_text('"ID","Kernel Name","Grid Size","gpu__time_duration.sum"\n"","","","us"\n'
+                   '"0","void irsde::<unnamed>::conv_tc_persist_kernel<(int)64, (int)2, (int)1, (int)6>(CUtensorMap_st)","(148, 1, 1)","10"\n'
+                   '"1","void irsde::<unnamed>::conv_tc_persist_kernel<(int)256, (int)0, (int)2, (int)12>(CUtensorMap_st)","(148, 1, 1)","20"\n')
+    script = os.path.join(ROOT, "scripts", "ncu_summarize.py")
+    ok = subprocess.run([sys.executable, script, str(raw), "--require", r"conv_tc_persist_kernel<\d+, 2[,>]", "--meta",
+                         str(tmp_path / "m.json"), "commit=abc"], capture_output=True, text=True)
+    assert ok.returncode == 0 and "gpu__time_duration.sum" in ok.stdout
+    meta = json.load(open(tmp_path / "m.json"))
+    assert meta["commit"] == "abc" and meta["kernel_mix"] == {"conv_tc_persist_kernel<64, 2, 1, 6>": 1, "conv_tc_persist_kernel<256, 0, 2, 12>": 1}
+    bad = subprocess.run([sys.executable, script, str(raw), "--require", r"conv_tc_persist_kernel<\d+, 3[,>]"], capture_output=True, text=True)
+    assert bad.returncode == 3 and "no kernel matches" in bad.stderr
