@@ -124,48 +124,6 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict_
   }
 }
 
-// statistics-only pass for the LayerNorm fold: same lane-group layout as layernorm_vec_kernel, writes (mean, rstd) per pixel
-template <typename T, int MAXV>
-__global__ void __launch_bounds__(256) ln_stats_kernel(const T* __restrict__ x, int x_pitch, float2* __restrict__ stats,
-                                                       long long npix, int C, int lpp) {
-  PDL_ENTRY();
-  constexpr int N = VecIO<T>::N;
-  const int lane = threadIdx.x & 31;
-  const int ppw = 32 / lpp;
-  const long long warp_g = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const long long pix = warp_g * ppw + lane / lpp;
-  const int sub = lane % lpp;
-  const int nvec = C / N;
-  const bool valid = pix < npix;
-  float v[MAXV][N];
-  float s = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int i = sub + k * lpp;
-    if (valid && i < nvec) {
-      VecIO<T>::load(x + pix * x_pitch + i * N, v[k]);
-#pragma unroll
-      for (int j = 0; j < N; ++j) s += v[k][j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < N; ++j) v[k][j] = 0.f;
-    }
-  }
-  for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)C;
-  float q = 0.f;
-#pragma unroll
-  for (int k = 0; k < MAXV; ++k) {
-    const int i = sub + k * lpp;
-    if (i < nvec) {
-#pragma unroll
-      for (int j = 0; j < N; ++j) { float d = v[k][j] - mean; q += d * d; }
-    }
-  }
-  for (int o = lpp >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  if (valid && sub == 0) stats[pix] = make_float2(mean, 1.0f / sqrtf(q / (float)C + 1e-5f));
-}
-
 // scalar fallback (any C / alignment): one warp per pixel, three cached passes
 template <typename T>
 __global__ void layernorm_scalar_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
@@ -231,35 +189,6 @@ void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int
   else LN_LAUNCH(16);
 #undef LN_LAUNCH
 }
-// (mean, rstd) per pixel; returns silently without launching when the vector path does not apply - callers check
-// ln_stats_supported() at plan-build time and fall back to the separate LayerNorm pass
-bool ln_stats_supported(int C, int x_pitch, const void* x) {
-  constexpr int N = 8;  // bf16 vectors
-  if (C % N || x_pitch % N || ((uintptr_t)x % 16)) return false;
-  int nvec = C / N, lpp = 1;
-  while (lpp * 2 <= 32 && lpp * 2 <= nvec) lpp *= 2;
-  return (nvec + lpp - 1) / lpp <= 16;
-}
-template <typename T>
-void launch_ln_stats(const T* x, int x_pitch, float* stats, long long npix, int C, cudaStream_t st) {
-  constexpr int N = VecIO<T>::N;
-  int nvec = C / N, lpp = 1;
-  while (lpp * 2 <= 32 && lpp * 2 <= nvec) lpp *= 2;
-  const int per_lane = (nvec + lpp - 1) / lpp;
-  const int warps = 8;
-  long long pix_per_block = (long long)warps * (32 / lpp);
-  unsigned grid = (unsigned)((npix + pix_per_block - 1) / pix_per_block);
-  float2* s2 = reinterpret_cast<float2*>(stats);
-#define LNS_LAUNCH(MV) pdl_launch(ln_stats_kernel<T, MV>, grid, warps * 32, 0, st, x, x_pitch, s2, npix, C, lpp)
-  if (per_lane <= 1) LNS_LAUNCH(1);
-  else if (per_lane <= 2) LNS_LAUNCH(2);
-  else if (per_lane <= 4) LNS_LAUNCH(4);
-  else if (per_lane <= 8) LNS_LAUNCH(8);
-  else LNS_LAUNCH(16);
-#undef LNS_LAUNCH
-}
-template void launch_ln_stats<bf16>(const bf16*, int, float*, long long, int, cudaStream_t);
-
 template void launch_layernorm<float>(const float*, int, const float*, const float*, int, float*, int, long long, int,
                                       cudaStream_t, const LnMod*);
 template void launch_layernorm<bf16>(const bf16*, int, const float*, const bf16*, int, bf16*, int, long long, int,

@@ -194,13 +194,6 @@ void launch_split_tf32(const float* in, int in_pitch, float* out, long long npix
 bool tc_fused_attention_available();
 void tc_conv_destroy(TcConvDesc*);
 void tc_conv_set_runtime(TcConvDesc*, const float* ss, const int* t_ptr, int ss_img_stride);
-// PreNorm LayerNorm folded into the to_qkv conv: stats = [npix][2] (mean, rstd) of the conv input, svec[n] = sum_c W'[n][c];
-// the descriptor must have been created with weights W' = W * diag(g) on the RAW input.  False: shape not supported.
-bool tc_conv_set_lnfold(TcConvDesc*, const float* stats_mean_rstd, const float* svec);
-// per-pixel channel statistics of an NHWC view: stats[p] = (mean, 1/sqrt(var + 1e-5))   (module_util.py:70-79)
-template <typename T>
-void launch_ln_stats(const T* x, int x_pitch, float* stats, long long npix, int C, cudaStream_t st);
-bool ln_stats_supported(int C, int x_pitch, const void* x);
 void tc_conv_set_out_nchw(TcConvDesc*, float* out, int cropH, int cropW);  // out==nullptr at create => fp32 NCHW output
 int tc_conv_launch(TcConvDesc*, cudaStream_t st);  // returns number of launches (1), <0 on error
 bool tc_init(std::string* err);                    // resolves cuTensorMapEncodeTiled

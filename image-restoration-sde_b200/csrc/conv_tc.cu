@@ -56,8 +56,6 @@ struct TcParams {
   // tile decode without integer divisions (they cost ~25 instructions + a MUFU.RCP each, five per tile and warp: on layers
   // with one k-iteration per tile the kernel was ISSUE-bound on them, ncu r02): q = umulhi(x, mg) with mg = ceil(2^32 / d)
   unsigned mg_tiles_m, mg_tiles_n, mg_tilesW, mg_tilesH, mg_B, mg_pairs_m;  // 0: divisor is 1 (or fast path not provable): see fdiv
-  const float2* ln_stats;  // LayerNorm fold (EK_LN): per input pixel (mean, rstd) of the conv INPUT
-  const float* ln_s;       // LayerNorm fold: s[n] = sum_c W'[n][c] (W' = W * diag(g), as rounded to bf16)
   int epi_kind;         // EK_* combination the epilogue is specialised for (EK_GENERIC: every feature checked at run time)
   int n_fast;           // tile order: N tiles of one M tile are consecutive (1x1 convs with several N tiles, see tc_conv_create)
   int tiles_n;
@@ -338,10 +336,7 @@ struct TileCoord {
 };
 // x / d for 0 <= x with x * d < 2^32 (host-checked in tc_fill_magic; mg == 0 selects the plain division)
 __device__ __forceinline__ int fdiv(int x, int d, unsigned mg) { return mg ? (int)__umulhi((unsigned)x, mg) : x / d; }
-// EK_LN: PreNorm LayerNorm folded into a 1x1 conv (module_util.py:82-90 + :157): LN_c(x) * g -> conv(W) ==
-// rstd_p * (conv(W * diag(g))(x) - mean_p * s[n]); the conv reads the RAW activations, a read-only statistics pass
-// replaces the read+write LayerNorm pass.  Only exists as a specialised kind (never under EK_GENERIC).
-enum { EK_QSM = 1, EK_AFF = 2, EK_SILU = 4, EK_RES = 8, EK_GENERIC = 16, EK_LN = 32 };
+enum { EK_QSM = 1, EK_AFF = 2, EK_SILU = 4, EK_RES = 8, EK_GENERIC = 16 };
 
 __device__ __forceinline__ void decode_m(const TcParams& P, int m_idx, TileCoord& t) {
   int q = fdiv(m_idx, P.tilesW, P.mg_tilesW);
@@ -678,10 +673,6 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
     uint8_t* const stg_base = smem_stg + (warp - 2) * 2048 * (Cfg::STG_BUFS > 0 ? Cfg::STG_BUFS : 1);
     int stg_i = 0;  // staging tile used by the next bulk store (alternates when STG_BUFS == 2)
     long long w_tfull = 0, t_start = clock64();
-    if constexpr (EKT != EK_GENERIC && (EKT & EK_LN)) {  // s[n] for every output channel, once per CTA (reuses the affine table)
-      for (int j = et; j < P.Cout && j < Cfg::EPI_FLOATS; j += 256) s_epi[j] = P.ln_s[j];
-      asm volatile("bar.sync 1, 256;" ::: "memory");
-    }
     int lt = 0, epi_n0 = -1, epi_b = -1;
     int seg_st = 0;  // fp32x3: K segments consumed by this warp (TMEM buffer = seg_st & 1)
     for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++lt) {
@@ -716,21 +707,9 @@ __global__ void __launch_bounds__(320, 1) conv_tc_persist_kernel(const __grid_co
       // KC: std::integral_constant<int, KIND>.  KIND = the EK_* features this conv has, fixed per launch: feature blocks
       // outside KIND do not exist in the instantiation (the compiler had turned several of them into predicated code that
       // was issued for every chunk), EK_GENERIC keeps every run-time check (fp32 NCHW output, no-TMA-store fallback).
-      float ln_mu = 0.f, ln_r = 0.f;
-      if constexpr (EKT != EK_GENERIC && (EKT & EK_LN)) {
-        if (pvalid) {
-          const float2 st2 = P.ln_stats[((long long)t.b * P.H + hh) * P.W + ww];
-          ln_mu = st2.x; ln_r = st2.y;
-        }
-      }
       auto process = [&](auto KC, uint32_t* v, const int c0) __attribute__((always_inline)) {
         constexpr int KIND = decltype(KC)::value;
         constexpr bool GEN = KIND == EK_GENERIC;
-        if constexpr (!GEN && (KIND & EK_LN)) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            v[j] = __float_as_uint(ln_r * fmaf(-ln_mu, s_epi[t.n0 + c0 + j], __uint_as_float(v[j])));
-        }
         if constexpr (TF3) {  // fp32 in, fp32 out: IEEE arithmetic, no fast-math approximations
           if (affine) {
 #pragma unroll
@@ -987,7 +966,6 @@ bool tc_init(std::string* err) {
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0, 1, EK_AFF>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0, 1, EK_QSM>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
-  cudaFuncSetAttribute(conv_tc_persist_kernel<128, 0, 1, EK_QSM | EK_LN>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 0>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<32, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<32, 3>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<64, 3>::SMEM_BYTES);
   cudaFuncSetAttribute(conv_tc_persist_kernel<128, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcCfgP<128, 3>::SMEM_BYTES);
@@ -1291,15 +1269,6 @@ void tc_conv_set_out_nchw(TcConvDesc* d, float* out, int cropH, int cropW) {
   d->P.cropW = cropW;
 }
 
-// LayerNorm fold (EK_LN) of a to_qkv conv: only the <128, 0, 1, EK_QSM | EK_LN> instantiation implements it
-bool tc_conv_set_lnfold(TcConvDesc* d, const float* stats_mean_rstd, const float* svec) {
-  if (d->mode != 0 || d->pair || d->BN != 128 || d->P.epi_kind != EK_QSM || d->P.Cout > 3 * 128 || d->P.ntaps != 1) return false;
-  d->P.ln_stats = reinterpret_cast<const float2*>(stats_mean_rstd);
-  d->P.ln_s = svec;
-  d->P.epi_kind = EK_QSM | EK_LN;
-  return true;
-}
-
 void tc_conv_set_runtime(TcConvDesc* d, const float* ss, const int* t_ptr, int ss_img_stride) {
   d->P.ss = ss;
   d->P.t_ptr = t_ptr;
@@ -1390,7 +1359,6 @@ int tc_conv_launch(TcConvDesc* d, cudaStream_t st) {
         case 128:
           if (ek == 0) TC_LAUNCH_EK(128, 0);
           else if (ek == EK_AFF) TC_LAUNCH_EK(128, EK_AFF);
-          else if (d->P.epi_kind == (EK_QSM | EK_LN)) TC_LAUNCH_EK(128, EK_QSM | EK_LN);  // not optional: the fold lives only here
           else if (ek == EK_QSM) TC_LAUNCH_EK(128, EK_QSM);
           else TC_LAUNCH(128, 0);
           break;

@@ -105,7 +105,6 @@ struct irsde_ctx {
   bool finalized = false;
   std::map<std::string, float*> w_simt;  // [KH*KW][Cin][Cout] fp32
   std::map<std::string, bf16*> w_tc;     // [phase][tap][Cout][Cin] bf16
-  std::map<std::string, float*> ln_svec;  // LayerNorm fold: s[n] of "<to_qkv weight name>" (w_tc holds W' under name + "#ln")
   std::map<std::string, float*> w_tc3;   // fp32x3: [phase][tap][2 (hi,lo)][Cout_pad][Cin] fp32 (tf32-rounded parts)
   bool use_tc3 = false;                  // fp32x3 mode: fp32 storage, convs through 3 x tcgen05.mma.kind::tf32
   std::map<std::string, int> ss_off;
@@ -278,27 +277,6 @@ __global__ void pack_tc3_up_kernel(const float* __restrict__ w, float* __restric
   long long base = (((long long)(phase * 4 + tap) * 2) * Cout_pad + co) * Cin + c;
   o[base] = hi;
   o[base + (long long)Cout_pad * Cin] = rn_tf32_w(acc - hi);
-}
-
-// LayerNorm fold of a to_qkv conv (1x1, [Cout][Cin]): W'[n][c] = bf16(w[n][c] * g[c]); s[n] = sum_c float(W'[n][c])
-__global__ void pack_tc_lnfold_kernel(const float* __restrict__ w, const float* __restrict__ g, bf16* __restrict__ o,
-                                      float* __restrict__ svec, int Cout, int Cin) {
-  const int n = blockIdx.x;
-  if (n >= Cout) return;
-  float acc = 0.f;
-  for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
-    const bf16 v = __float2bfloat16_rn(w[(long long)n * Cin + c] * g[c]);
-    o[(long long)n * Cin + c] = v;
-    acc += __bfloat162float(v);
-  }
-  __shared__ float red[256];
-  red[threadIdx.x] = acc;
-  __syncthreads();
-  for (int o2 = 128; o2 > 0; o2 >>= 1) {
-    if ((int)threadIdx.x < o2) red[threadIdx.x] += red[threadIdx.x + o2];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) svec[n] = red[0];
 }
 
 // ---- architecture description --------------------------------------------------------------------
@@ -766,35 +744,9 @@ struct Builder {
   void attention(const std::string& pre, V in, V out, int H, int W, bool full, float* la_partial, float* la_ctx) {
     int C = in.C, B = plan->B, N = H * W;
     long long npix = (long long)B * N;
-    irsde_ctx* c = ctx;
-    if constexpr (std::is_same<T, bf16>::value) {
-      // PreNorm folded into to_qkv: stats pass (read-only) + conv on the raw input with W * diag(g); see conv_tc.cu EK_LN
-      const std::string wq = pre + "fn.fn.to_qkv.weight";
-      static const bool lnfold_on = !(getenv("IRSDE_LNFOLD") && getenv("IRSDE_LNFOLD")[0] == '0');
-      if (lnfold_on && !full && ctx->use_tc && tc_fused_attention_available() && C % 8 == 0 && ctx->w_tc.count(wq + "#ln") &&
-          ln_stats_supported(C, in.pitch, in.p) && (long long)B * ((H * W + 127) / 128) * 3 >= 1) {
-        float* stats = (float*)dev_alloc(ctx, (size_t)npix * 2 * sizeof(float), &plan->allocs);
-        if (!stats) { ok = false; err = "cudaMalloc failed"; return; }
-        plan->ops.push_back(OpRec{CAT_LN, 0.0, [=](Plan*, cudaStream_t st) {
-          launch_ln_stats<bf16>((const bf16*)in.p, in.pitch, stats, npix, C, st);
-          c->launches++;
-        }});
-        plan->ops.back().label = pre + "norm stats (LN folded into to_qkv)";
-        plan->ops.back().bytes = (double)npix * C * sizeof(T) + npix * 8.0;
-        T* qkv = tmp(npix * 384);
-        size_t before = plan->tc_descs.size();
-        conv(wq, in, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384, nullptr, TC_FLAG_QSOFTMAX,
-             (const bf16*)ctx->w_tc[wq + "#ln"]);
-        if (!ok) return;
-        if (plan->tc_descs.size() != before + 1 || !tc_conv_set_lnfold(plan->tc_descs.back(), stats, ctx->ln_svec[wq])) {
-          ok = false; err = "LayerNorm fold not applicable to " + wq; return;
-        }
-        attention_tail(pre, in, out, H, W, qkv, la_partial, la_ctx);
-        return;
-      }
-    }
     T* xn = tmp(npix * C);
     float* g1 = fw(pre + "fn.norm.g");
+    irsde_ctx* c = ctx;
     plan->ops.push_back(OpRec{CAT_LN, 0.0, [=](Plan*, cudaStream_t st) {
       launch_layernorm<T>(in.p, in.pitch, g1, nullptr, 0, xn, C, npix, C, st);
       c->launches++;
@@ -811,22 +763,6 @@ struct Builder {
         conv(pre + "fn.fn.to_qkv.weight", V{xn, C, C}, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384, nullptr,
              TC_FLAG_QSOFTMAX);
         release(xn);
-        attention_tail(pre, in, out, H, W, qkv, la_partial, la_ctx);
-        return;
-      }
-    }
-    conv(pre + "fn.fn.to_qkv.weight", V{xn, C, C}, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384);
-    attention_rest(pre, in, out, H, W, full, la_partial, la_ctx, xn, qkv);
-  }
-
-  // fused LinearAttention after to_qkv: k,v -> ctx, ctx folded into per-image to_out weights, ONE per-image-weight GEMM,
-  // LayerNorm + residual (module_util.py:163-178 with the two einsums + to_out conv re-associated)
-  void attention_tail(const std::string& pre, V in, V out, int H, int W, T* qkv, float* la_partial, float* la_ctx) {
-    int C = in.C, B = plan->B, N = H * W;
-    long long npix = (long long)B * N;
-    irsde_ctx* c = ctx;
-    if constexpr (std::is_same<T, bf16>::value) {
-      {
         plan->ops.push_back(OpRec{CAT_ATTN, 0.0, [=](Plan*, cudaStream_t st) {
           launch_linattn_ctx<T>(qkv, 384, la_partial, la_ctx, B, N, st);
           c->launches += 2;
@@ -860,14 +796,7 @@ struct Builder {
         return;
       }
     }
-    (void)c; (void)npix; (void)N;
-  }
-
-  // unfused remainder (fp32 modes, full softmax Attention): to_qkv already issued by the caller
-  void attention_rest(const std::string& pre, V in, V out, int H, int W, bool full, float* la_partial, float* la_ctx, T* xn, T* qkv) {
-    int C = in.C, B = plan->B, N = H * W;
-    long long npix = (long long)B * N;
-    irsde_ctx* c = ctx;
+    conv(pre + "fn.fn.to_qkv.weight", V{xn, C, C}, H, W, 1, 1, 0, 1, nullptr, "", 0, nullptr, V{qkv, 384, 384}, 384);
     release(xn);
     T* hid = tmp(npix * 128);
     if (full) {
@@ -1808,23 +1737,6 @@ int irsde_finalize_weights(irsde_ctx* ctx) {
         pack_tc_padded_kernel<<<(unsigned)((nt + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cout_pad, Cin, KH, KW);
       else
         pack_tc_kernel<<<(unsigned)((n + 255) / 256), 256>>>(ctx->raw[s.name].dev, wt, Cout, Cin, KH, KW);
-    }
-  }
-  // LayerNorm fold (bf16 tensor-core path): to_qkv weights pre-multiplied by the PreNorm gain, plus their row sums
-  if (ctx->cfg.precision == IRSDE_PREC_BF16) {
-    for (auto& sp : specs) {
-      const std::string suf = "fn.fn.to_qkv.weight";
-      if (sp.name.size() < suf.size() || sp.name.compare(sp.name.size() - suf.size(), suf.size(), suf) != 0) continue;
-      const std::string gname = sp.name.substr(0, sp.name.size() - suf.size()) + "fn.norm.g";
-      auto git = ctx->raw.find(gname);
-      if (git == ctx->raw.end()) continue;
-      const int Cout = (int)sp.shape[0], Cin = (int)sp.shape[1];
-      bf16*& wl = ctx->w_tc[sp.name + "#ln"];
-      float*& sv = ctx->ln_svec[sp.name];
-      if (!wl) wl = (bf16*)dev_alloc(ctx, (size_t)Cout * Cin * 2, &ctx->allocs);
-      if (!sv) sv = (float*)dev_alloc(ctx, (size_t)Cout * 4, &ctx->allocs);
-      if (!wl || !sv) return fail(ctx, IRSDE_ERR_CUDA, "cudaMalloc failed");
-      pack_tc_lnfold_kernel<<<Cout, 256>>>(ctx->raw[sp.name].dev, git->second.dev, wl, sv, Cout, Cin);
     }
   }
   // time-modulation: concatenate every block's mlp.1 into one [S][td_in] matrix
