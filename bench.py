@@ -127,10 +127,13 @@ def ncu_traffic_per_launch():
             pass
         bi = build_info()
         same = bool(meta.get("csrc_sha256")) and meta.get("csrc_sha256") == bi.get("csrc_sha256")
+        same_conv = bool(meta.get("conv_tc_sha256")) and meta.get("conv_tc_sha256") == bi.get("conv_tc_sha256")
         src = ("%s: mean dram read+write bytes per launch over %d launches of one step, ncu --set full; captured from commit %s "
-               "(csrc %s); this build: commit %s (csrc %s) -> %s" % (
+               "(csrc %s, conv_tc %s); this build: commit %s (csrc %s, conv_tc %s) -> %s" % (
                    os.path.relpath(path, ROOT), len(rows), meta.get("commit", "?"), meta.get("csrc_sha256", "?"),
-                   bi.get("commit", "?"), bi.get("csrc_sha256", "?"), "same sources" if same else "DIFFERENT sources"))
+                   meta.get("conv_tc_sha256", "?"), bi.get("commit", "?"), bi.get("csrc_sha256", "?"), bi.get("conv_tc_sha256", "?"),
+                   "same sources" if same else ("same conv kernel sources (conv_tc.cu + common.cuh), other kernels changed" if same_conv
+                                                else "DIFFERENT sources")))
         return tot * 1e6 / len(rows), src
     except Exception as e:
         return None, "unreadable %s: %s" % (path, e)

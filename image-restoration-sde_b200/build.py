@@ -32,6 +32,18 @@ def csrc_sha256():
     return h.hexdigest()[:16]
 
 
+def conv_tc_sha256(read=None):
+    """Hash of the sources the tcgen05 conv kernel compiles from (conv_tc.cu + common.cuh): a conv capture stays valid across
+    builds that only touch the other kernels."""
+    import hashlib
+    read = read or (lambda f: open(os.path.join(CSRC, f), "rb").read())
+    h = hashlib.sha256()
+    for f in ("common.cuh", "conv_tc.cu"):
+        h.update(f.encode())
+        h.update(read(f))
+    return h.hexdigest()[:16]
+
+
 def _write_build_info():
     try:
         commit = subprocess.run(["git", "-C", HERE, "rev-parse", "--short", "HEAD"], capture_output=True, text=True).stdout.strip()
@@ -47,7 +59,8 @@ def _write_build_info():
         except Exception:
             pass
     with open(os.path.join(HERE, "BUILD_INFO"), "w") as f:
-        f.write("commit=%s%s\ncsrc_sha256=%s\n" % (commit or "unknown", "+dirty" if dirty else "", csrc_sha256()))
+        f.write("commit=%s%s\ncsrc_sha256=%s\nconv_tc_sha256=%s\n" % (commit or "unknown", "+dirty" if dirty else "", csrc_sha256(),
+                                                                       conv_tc_sha256()))
 
 
 def build(force=False, verbose=False):

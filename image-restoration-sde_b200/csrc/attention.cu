@@ -2,11 +2,29 @@
 // (module_util.py:150-178) and the full softmax Attention of the denoising-sde variant (:182-204).
 // All loads/stores are 128-bit vectors over the NHWC channel dimension; math is fp32.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 
 namespace irsde {
+
+// Round-2b kernels of this file, one bit each (IRSDE_HBM_NEW; 0 = the round-2a kernels, kept for same-box A/B runs and as
+// the reference scripts/hbm_probe.py compares against).  IRSDE_HBM_DEFAULT is the setting validated on the GPU.
+//   1 = LayerNorm with compile-time lane geometry     2 = la_combine with 128-bit record loads
+//   4 = la_fold with 16 output rows per block          8 = k/v pass with warp-shuffle softmax statistics (2 block barriers)
+#define IRSDE_HBM_DEFAULT 0
+#define IRSDE_LN_PP_DEFAULT 2
+static int hbm_mask_from_env() {
+  const char* e = getenv("IRSDE_HBM_NEW");
+  return e && *e ? atoi(e) : IRSDE_HBM_DEFAULT;
+}
+static const int g_hbm_new = hbm_mask_from_env();
+static int ln_pp_from_env() {  // pixels per lane group of layernorm_geo_kernel (rows of <= 2 vectors per lane)
+  const char* e = getenv("IRSDE_LN_PP");
+  return e && *e ? (*e == '1' ? 1 : 2) : IRSDE_LN_PP_DEFAULT;
+}
+static const int g_ln_pp = ln_pp_from_env();
 
 // accurate exp in parity (fp32) mode, fast exp in perf (bf16) mode
 template <typename T>
@@ -22,6 +40,9 @@ struct VecIO;
 template <>
 struct VecIO<float> {
   static constexpr int N = 4;
+  typedef float4 Raw;  // a vector as loaded (unpacked late to keep registers down)
+  static __device__ __forceinline__ Raw load_raw(const float* p) { return *reinterpret_cast<const float4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float* v) { v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
   static __device__ __forceinline__ void load(const float* p, float* v) {
     float4 t = *reinterpret_cast<const float4*>(p);
     v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
@@ -33,6 +54,13 @@ struct VecIO<float> {
 template <>
 struct VecIO<bf16> {
   static constexpr int N = 8;
+  typedef uint4 Raw;
+  static __device__ __forceinline__ Raw load_raw(const bf16* p) { return *reinterpret_cast<const uint4*>(p); }
+  static __device__ __forceinline__ void unpack(const Raw& t, float* v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { v[2 * i] = __low2float(h[i]); v[2 * i + 1] = __high2float(h[i]); }
+  }
   static __device__ __forceinline__ void load(const bf16* p, float* v) {
     uint4 t = *reinterpret_cast<const uint4*>(p);
     const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&t);
@@ -124,6 +152,96 @@ __global__ void __launch_bounds__(256) layernorm_vec_kernel(const T* __restrict_
   }
 }
 
+// Round-2b LayerNorm.  ncu on the kernel above (profiles/r02_hbm_kernels_ncu_full.csv): 2.9-4.1 TB/s at SM throughput 82-84 % -
+// it is bound by the instructions it ISSUES per 16-byte vector (run-time lane geometry: integer divisions, shuffle loops
+// with branches, per-vector bounds checks, IEEE divide / sqrt slow-path scaffolding), not by bytes in flight.  Here the
+// geometry is a template parameter (C == N * LPP * MAXV exactly, lane / LPP are shifts, shuffle trees unrolled), a lane
+// group owns PP pixels so the gain row and the address set-up are shared, the residual row is requested together with x,
+// out-of-range pixels are clamped to the last valid one (loads stay unpredicated, only the store is guarded), and the bf16
+// (perf) instantiation uses mean = s * (1/C) and rsqrtf.  The fp32 instantiations keep the IEEE forms and the operation
+// order of the kernel above, so fp32 / fp32x3 results are unchanged bit for bit.
+template <typename T, int MAXV, int LPP, int PP>
+__global__ void __launch_bounds__(256, (MAXV * PP <= 2 ? 4 : (MAXV * PP <= 4 ? 2 : 1))) layernorm_geo_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
+                                                            const T* __restrict__ res, int res_pitch, T* __restrict__ out,
+                                                            int out_pitch, long long npix, int C, float inv_C, LnMod mod) {
+  PDL_ENTRY();
+  constexpr int N = VecIO<T>::N;
+  constexpr int PPW = 32 / LPP;               // pixels per warp and pass
+  constexpr bool FAST = sizeof(T) == 2;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane % LPP;
+  const long long pix0 = ((long long)blockIdx.x * PP * 8 + (threadIdx.x >> 5)) * PPW + lane / LPP;
+  float v[PP][MAXV][N];
+  typename VecIO<T>::Raw r[PP][MAXV];
+  long long pixc[PP];
+  bool valid[PP];
+#pragma unroll
+  for (int p = 0; p < PP; ++p) {
+    const long long pix = pix0 + (long long)p * 8 * PPW;
+    valid[p] = pix < npix;
+    pixc[p] = valid[p] ? pix : npix - 1;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) VecIO<T>::load(x + pixc[p] * x_pitch + (sub + k * LPP) * N, v[p][k]);
+  }
+  if (res) {
+#pragma unroll
+    for (int p = 0; p < PP; ++p)
+#pragma unroll
+      for (int k = 0; k < MAXV; ++k) r[p][k] = VecIO<T>::load_raw(res + pixc[p] * res_pitch + (sub + k * LPP) * N);
+  }
+  float gg[MAXV][N];
+#pragma unroll
+  for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+    for (int j = 0; j < N; j += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(g + (sub + k * LPP) * N + j);
+      gg[k][j] = t.x; gg[k][j + 1] = t.y; gg[k][j + 2] = t.z; gg[k][j + 3] = t.w;
+    }
+  float rstd[PP];
+#pragma unroll
+  for (int p = 0; p < PP; ++p) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+      for (int j = 0; j < N; ++j) s += v[p][k][j];
+#pragma unroll
+    for (int o = LPP >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = FAST ? s * inv_C : s / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+#pragma unroll
+      for (int j = 0; j < N; ++j) { v[p][k][j] -= mean; q += v[p][k][j] * v[p][k][j]; }
+#pragma unroll
+    for (int o = LPP >> 1; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    rstd[p] = FAST ? rsqrtf(q * inv_C + 1e-5f) : 1.0f / sqrtf(q / (float)C + 1e-5f);
+  }
+#pragma unroll
+  for (int p = 0; p < PP; ++p) {
+    const float* mrow = nullptr;  // NAFBlock time modulation: y * (scale + 1) + shift  (DenoisingNAFNet_arch.py:62-63,75-76)
+    if (mod.ss) mrow = mod.ss + (long long)((mod.t_ptr ? *mod.t_ptr : 0) + (int)(pixc[p] / mod.pix_per_img) * mod.img_stride) * mod.S;
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k) {
+      const int c0 = (sub + k * LPP) * N;
+      float y[N];
+#pragma unroll
+      for (int j = 0; j < N; ++j) y[j] = v[p][k][j] * rstd[p] * gg[k][j];
+      if (mrow) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) y[j] = y[j] * (mrow[mod.off_scale + c0 + j] + 1.0f) + mrow[mod.off_shift + c0 + j];
+      }
+      if (res) {
+        float rr[N];
+        VecIO<T>::unpack(r[p][k], rr);
+#pragma unroll
+        for (int j = 0; j < N; ++j) y[j] += rr[j];
+      }
+      if (valid[p]) VecIO<T>::store(out + pixc[p] * out_pitch + c0, y);
+    }
+  }
+}
+
 // scalar fallback (any C / alignment): one warp per pixel, three cached passes
 template <typename T>
 __global__ void layernorm_scalar_kernel(const T* __restrict__ x, int x_pitch, const float* __restrict__ g,
@@ -179,6 +297,26 @@ void launch_layernorm(const T* x, int x_pitch, const float* g, const T* res, int
   }
   const int warps = 8;
   long long pix_per_block = (long long)warps * (32 / lpp);
+  if ((g_hbm_new & 1) && nvec == lpp * per_lane && (per_lane & (per_lane - 1)) == 0 && lpp >= 8 && npix > 0) {
+    // exact geometry: C == N * LPP * MAXV.  PP pixels per lane group (IRSDE_LN_PP, default 2) while the row fits 2 vectors per lane.
+#define LN_GEO(MV, LP, PPX)                                                                                              \
+  pdl_launch(layernorm_geo_kernel<T, MV, LP, PPX>, (unsigned)((npix + pix_per_block * PPX - 1) / (pix_per_block * PPX)),   \
+             warps * 32, 0, st, x, x_pitch, g, res, res_pitch, out, out_pitch, npix, C, 1.0f / (float)C, mod)
+#define LN_GEO_PP(MV, LP)                \
+  do {                                   \
+    if (g_ln_pp == 2) LN_GEO(MV, LP, 2); \
+    else LN_GEO(MV, LP, 1);              \
+    return;                              \
+  } while (0)
+    if (lpp == 8 && per_lane == 1) LN_GEO_PP(1, 8);
+    if (lpp == 16 && per_lane == 1) LN_GEO_PP(1, 16);
+    if (lpp == 32 && per_lane == 1) LN_GEO_PP(1, 32);
+    if (lpp == 32 && per_lane == 2) LN_GEO_PP(2, 32);
+    if (lpp == 32 && per_lane == 4) { LN_GEO(4, 32, 1); return; }
+    if (lpp == 32 && per_lane == 8 && sizeof(T) == 4) { LN_GEO(8, 32, 1); return; }
+#undef LN_GEO_PP
+#undef LN_GEO
+  }
   unsigned grid = (unsigned)((npix + pix_per_block - 1) / pix_per_block);
 #define LN_LAUNCH(MV) \
   pdl_launch(layernorm_vec_kernel<T, MV>, grid, warps * 32, 0, st, x, x_pitch, g, res, res_pitch, out, out_pitch, npix, C, lpp, mod)
@@ -348,6 +486,57 @@ __global__ void __launch_bounds__(256) la_combine_kernel(const float* __restrict
   ctx[(long long)bh * 1024 + tid] = acc / S / (float)N;
 }
 
+// Round-2b merge.  la_combine_kernel above issues 192 scalar requests per thread (1 536 per block / SM): the time (19 us for
+// 5 MB under ncu) is the SM's outstanding-request limit, not latency of a single chain.  Here one WARP owns 4 d-rows of one
+// (image, head) = 128 ctx entries as one float4 per lane: the 64 records' (m, s) for those rows come in as two float4 loads
+// per lane and are shared through shared memory, and each record's ctx slice is ONE 128-bit request per lane, 32 records
+// in flight.  Per entry the arithmetic and its order are those of la_combine_kernel (bit-identical ctx).
+__global__ void __launch_bounds__(32) la_combine4_kernel(const float* __restrict__ part, float* __restrict__ ctx, int N, int nblk) {
+  PDL_ENTRY();
+  __shared__ __align__(16) float ms[LA_MAXBLK][4], ss[LA_MAXBLK][4];
+  const int bh = blockIdx.x >> 3, b = bh >> 2, h = bh & 3, d0 = (blockIdx.x & 7) * 4;
+  const int lane = threadIdx.x, dd = lane >> 3, e4 = (lane & 7) * 4;
+  const float* base = part + (long long)b * LA_MAXBLK * LA_REC + h * 1088;
+#pragma unroll
+  for (int k = lane; k < LA_MAXBLK; k += 32) {
+    float4 m4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < nblk) {
+      m4 = *reinterpret_cast<const float4*>(base + (long long)k * LA_REC + d0);
+      s4 = *reinterpret_cast<const float4*>(base + (long long)k * LA_REC + 32 + d0);
+    }
+    *reinterpret_cast<float4*>(ms[k]) = m4;
+    *reinterpret_cast<float4*>(ss[k]) = s4;
+  }
+  __syncwarp();
+  float M = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < LA_MAXBLK; ++k) M = fmaxf(M, ms[k][dd]);
+  const float* cbase = base + 64 + (d0 + dd) * 32 + e4;
+  float S = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int k0 = 0; k0 < LA_MAXBLK; k0 += 32) {
+    float4 ck[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      ck[j] = (k0 + j) < nblk ? *reinterpret_cast<const float4*>(cbase + (long long)(k0 + j) * LA_REC) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+      if (k0 + j < nblk) {
+        const float w = expf(ms[k0 + j][dd] - M);
+        S += ss[k0 + j][dd] * w;
+        acc.x += ck[j].x * w;
+        acc.y += ck[j].y * w;
+        acc.z += ck[j].z * w;
+        acc.w += ck[j].w * w;
+      }
+    }
+  }
+  const float fN = (float)N;
+  *reinterpret_cast<float4*>(ctx + (long long)bh * 1024 + (d0 + dd) * 32 + e4) =
+      make_float4(acc.x / S / fN, acc.y / S / fN, acc.z / S / fN, acc.w / S / fN);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) la_out_kernel(const T* __restrict__ qkv, int pitch, const float* __restrict__ ctx,
                                                      T* __restrict__ hidden, int hid_pitch, int N) {
@@ -415,6 +604,13 @@ __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
+// SHFL (round 2b): the softmax statistics of a chunk stay inside a warp.  Lane (qtr = lane / 4, cpl = lane % 4) of warp w
+// owns channel pairs w*4+cpl and 32+w*4+cpl on the 8 pixels px == qtr (mod 8): the running max / sum live in registers
+// (replicated over the 8 qtr lanes), the cross-pixel max and sum are three xor-shuffles each, and the bf16x2 accesses
+// (word = 4*px + pair mod 32) are bank-conflict free.  One chunk then needs TWO block barriers (tile landed / P and alpha
+// visible to the MMA warps) instead of five; ncu on the <false> form: 99 us for 268 MB with SM throughput 58 % - the
+// per-chunk barrier chain, not memory, was the bound.
+template <bool SHFL>
 __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__ qkv, int pitch, float* __restrict__ part,
                                                         int N, int nchunks, int nblk) {
   PDL_ENTRY();
@@ -457,6 +653,9 @@ __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__
   if (c0 < c1) issue_load(c0, 0);
   const int cp2 = (tid & 63) * 2, qtr = tid >> 6;  // stats mapping: 2 channels x 16 pixels per thread
   const float LOG2E = 1.4426950408889634f;
+  // SHFL mapping and register-resident running statistics: [0,1] = pair A (lo, hi channel), [2,3] = pair B
+  const int sq = lane >> 2, pA = warp * 4 + (lane & 3), pB = 32 + pA;
+  float mr[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sr[4] = {0.f, 0.f, 0.f, 0.f};
   for (int ch = c0; ch < c1; ++ch) {
     const int buf = (ch - c0) & 1;
     const bf16* T0 = tile + buf * LA_PIX * LAM_TP;
@@ -464,6 +663,54 @@ __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__
     __syncthreads();  // tile[buf] landed; everyone is done with tile[buf^1] and Ps of the previous chunk
     if (ch + 1 < c1) issue_load(ch + 1, buf ^ 1);
     const int nvalid = min(LA_PIX, N - ch * LA_PIX);
+    if constexpr (SHFL) {
+      __nv_bfloat162 kA[8], kB[8];
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int px = i * 8 + sq;
+        if (px < nvalid) {
+          kA[i] = *reinterpret_cast<const __nv_bfloat162*>(T0 + px * LAM_TP + 2 * pA);
+          kB[i] = *reinterpret_cast<const __nv_bfloat162*>(T0 + px * LAM_TP + 2 * pB);
+          mx[0] = fmaxf(mx[0], __low2float(kA[i]));
+          mx[1] = fmaxf(mx[1], __high2float(kA[i]));
+          mx[2] = fmaxf(mx[2], __low2float(kB[i]));
+          mx[3] = fmaxf(mx[3], __high2float(kB[i]));
+        }
+      }
+      float mn[4], ps[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
+        mn[c] = fmaxf(mr[c], mx[c]);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int px = i * 8 + sq;
+        __nv_bfloat162 qa = __floats2bfloat162_rn(0.f, 0.f), qb = qa;
+        if (px < nvalid) {
+          qa = __floats2bfloat162_rn(exp2f((__low2float(kA[i]) - mn[0]) * LOG2E), exp2f((__high2float(kA[i]) - mn[1]) * LOG2E));
+          qb = __floats2bfloat162_rn(exp2f((__low2float(kB[i]) - mn[2]) * LOG2E), exp2f((__high2float(kB[i]) - mn[3]) * LOG2E));
+          ps[0] += __low2float(qa);   // sum the rounded values the MMA will actually use
+          ps[1] += __high2float(qa);
+          ps[2] += __low2float(qb);
+          ps[3] += __high2float(qb);
+        }
+        *reinterpret_cast<__nv_bfloat162*>(Ps + px * LAM_PP + 2 * pA) = qa;
+        *reinterpret_cast<__nv_bfloat162*>(Ps + px * LAM_PP + 2 * pB) = qb;
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+#pragma unroll
+        for (int o = 4; o < 32; o <<= 1) ps[c] += __shfl_xor_sync(0xffffffffu, ps[c], o);
+        const float a = exp2f((mr[c] - mn[c]) * LOG2E);  // 0 on the first chunk
+        sr[c] = sr[c] * a + ps[c];
+        mr[c] = mn[c];
+        if (sq == 0) alpha_s[2 * (c < 2 ? pA : pB) + (c & 1)] = a;
+      }
+      __syncthreads();  // P and alpha visible to the MMA warps
+    } else {
     // ---- per-channel max over the chunk
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -509,6 +756,7 @@ __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__
       m_run[cp2 + 1] = mn1;
     }
     __syncthreads();
+    }  // !SHFL
     // ---- rescale and accumulate: rows g / g+8 of this warp's 16 d-rows
     {
       const float al_lo = alpha_s[dbase + (lane >> 2)], al_hi = alpha_s[dbase + (lane >> 2) + 8];
@@ -537,7 +785,16 @@ __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__
   }
   __syncthreads();
   float* rec = part + ((long long)b * LA_MAXBLK + blk) * LA_REC;
-  if (tid < 128) {
+  if constexpr (SHFL) {
+    if (sq == 0) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int chn = 2 * (c < 2 ? pA : pB) + (c & 1);
+        rec[(chn >> 5) * 1088 + (chn & 31)] = mr[c];
+        rec[(chn >> 5) * 1088 + 32 + (chn & 31)] = sr[c];
+      }
+    }
+  } else if (tid < 128) {
     const int hh = tid >> 5, dd = tid & 31;
     rec[hh * 1088 + dd] = m_run[tid];
     rec[hh * 1088 + 32 + dd] = s_run[tid];
@@ -568,7 +825,8 @@ template <>
 void launch_la_kv<bf16>(const bf16* qkv, int qkv_pitch, float* partial, int B, int N, int nchunks, int nblk, size_t smem,
                         cudaStream_t st) {
   if (qkv_pitch % 8 == 0 && ((uintptr_t)qkv % 16) == 0)
-    pdl_launch(la_kv_mma_kernel, dim3(nblk, B), 256, LAM_SMEM, st, qkv, qkv_pitch, partial, N, nchunks, nblk);
+    if (g_hbm_new & 8) pdl_launch(la_kv_mma_kernel<true>, dim3(nblk, B), 256, LAM_SMEM, st, qkv, qkv_pitch, partial, N, nchunks, nblk);
+    else pdl_launch(la_kv_mma_kernel<false>, dim3(nblk, B), 256, LAM_SMEM, st, qkv, qkv_pitch, partial, N, nchunks, nblk);
   else
     pdl_launch(la_kv_kernel<bf16>, dim3(nblk, B), 256, smem, st, qkv, qkv_pitch, partial, N, nchunks, nblk);
 }
@@ -581,11 +839,13 @@ void launch_linattn_ctx(const T* qkv, int qkv_pitch, float* partial, float* ctx,
   if (!g_la_attr_done) {
     cudaFuncSetAttribute(la_kv_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(la_kv_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(la_kv_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAM_SMEM);
+    cudaFuncSetAttribute(la_kv_mma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAM_SMEM);
+    cudaFuncSetAttribute(la_kv_mma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LAM_SMEM);
     g_la_attr_done = true;
   }
   launch_la_kv<T>(qkv, qkv_pitch, partial, B, N, nchunks, nblk, smem, st);
-  pdl_launch(la_combine_kernel, B * 4 * 4, 256, 0, st, partial, ctx, N, nblk);
+  if (g_hbm_new & 2) pdl_launch(la_combine4_kernel, B * 4 * 8, 32, 0, st, partial, ctx, N, nblk);
+  else pdl_launch(la_combine_kernel, B * 4 * 4, 256, 0, st, partial, ctx, N, nblk);
 }
 template void launch_linattn_ctx<float>(const float*, int, float*, float*, int, int, cudaStream_t);
 template void launch_linattn_ctx<bf16>(const bf16*, int, float*, float*, int, int, cudaStream_t);
@@ -617,8 +877,44 @@ __global__ void la_fold_kernel(const float* __restrict__ ctx, const float* __res
   for (int e = 0; e < 32; ++e) acc += w[e] * cs[h][d][e];
   Mb[((long long)b * C + c) * 128 + k] = __float2bfloat16_rn(acc);
 }
+// Round-2b fold: la_fold_kernel stages the image's whole 16 KB context in shared memory for TWO output rows (2 048 blocks x
+// 16 KB of L2 reads at C = 512).  Here a block owns 16 output rows: a thread keeps ITS context row (h, d, 0..31) in
+// registers (eight 128-bit loads, no staging), the 16 weight rows go through shared memory once, and all loads of the block
+// are one round trip.  Same per-entry sum order as above (bit-identical Mb).
+__global__ void __launch_bounds__(256) la_fold16_kernel(const float* __restrict__ ctx, const float* __restrict__ wout,
+                                                        bf16* __restrict__ Mb, int C) {
+  PDL_ENTRY();
+  __shared__ __align__(16) float ws[16][128];
+  const int b = blockIdx.y, cbase = blockIdx.x * 16, tid = threadIdx.x;
+  const int k = tid & 127, h = k >> 5, cc = tid >> 7;
+  float cr[32];
+  const float4* cp = reinterpret_cast<const float4*>(ctx + (long long)b * 4096 + k * 32);  // ctx[b][h][d][0..31], k = h*32+d
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 t = cp[j];
+    cr[4 * j] = t.x; cr[4 * j + 1] = t.y; cr[4 * j + 2] = t.z; cr[4 * j + 3] = t.w;
+  }
+#pragma unroll
+  for (int i = tid; i < 16 * 32; i += 256) {   // 16 rows x 32 float4
+    const int row = i >> 5, c = cbase + row;
+    reinterpret_cast<float4*>(&ws[row][0])[i & 31] =
+        c < C ? reinterpret_cast<const float4*>(wout + (long long)c * 128)[i & 31] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 2 + cc, c = cbase + row;
+    if (c >= C) continue;
+    const float* w = &ws[row][h * 32];
+    float acc = 0.f;
+#pragma unroll
+    for (int e = 0; e < 32; ++e) acc += w[e] * cr[e];
+    Mb[((long long)b * C + c) * 128 + k] = __float2bfloat16_rn(acc);
+  }
+}
 void launch_la_fold(const float* ctx, const float* wout, bf16* Mb, int B, int C, cudaStream_t st) {
-  pdl_launch(la_fold_kernel, dim3((C + 1) / 2, B), 256, 0, st, ctx, wout, Mb, C);
+  if (g_hbm_new & 4) pdl_launch(la_fold16_kernel, dim3((C + 15) / 16, B), 256, 0, st, ctx, wout, Mb, C);
+  else pdl_launch(la_fold_kernel, dim3((C + 1) / 2, B), 256, 0, st, ctx, wout, Mb, C);
 }
 
 // =============================================================================================
@@ -698,9 +994,9 @@ __global__ void __launch_bounds__(128) fullattn_kernel(const T* __restrict__ qkv
 // online softmax on the accumulator fragments (row max / sum across the 4 lanes of a quad by shuffles), P re-packed in
 // registers as the bf16 A operand of the second product (the FlashAttention-2 register reuse, no smem round trip),
 // O += P V with V fragments from ldmatrix.trans.  K and V tiles stream through a double-buffered cp.async ring.
-// Arithmetic intensity note: with d = 32 every score costs 64 tensor MACs but one ex2 on the 16/clk/SM
-// MUFU pipe, so this kernel is MUFU-bound by ~8x - the tensor pipe cannot exceed ~12 % here whatever the MMA flavour
-// (tcgen05 would not change that; it is why this stays on mma.sync, whose operands come straight from registers).
+// Measured (profiles/r02_fullattn_ncu_full.csv, 1 024 keys, 8 images): 38 us per launch, HMMA pipe 26 %, issue slots
+// 60 % busy at 20 % occupancy: with d = 32 every mma.sync is surrounded by ~6 softmax / re-pack instructions, so the issue
+// slots fill first (MUFU is at ~20 %).  It stays on mma.sync, whose operands come straight from registers.
 // ---------------------------------------------------------------------------------------------
 static const int FA_Q = 64, FA_K = 64, FA_P = 40;  // queries / keys per block; smem row pitch (32 + 8 pad, bf16)
 __device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
