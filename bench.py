@@ -550,7 +550,7 @@ def run_b200(args):
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": nbytes_in, "d2h_bytes_per_step": nbytes_out},
                 "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "breakdown": breakdown,
-                "device_bytes": sum(int(c.L.irsde_device_bytes(c.h)) for c in ctxs if c is not None), "build": build_info()}
+                "device_bytes": sum(int(c.L.irsde_device_bytes(c.h)) for c in ctxs if c is not None), "build": dict(build_info(), **{k: os.environ[k] for k in ("IRSDE_HBM_NEW", "IRSDE_LN_PP") if k in os.environ})}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

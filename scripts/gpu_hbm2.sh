@@ -7,15 +7,16 @@ mkdir -p gpurun_out
 . image-restoration-sde_b200/BUILD_INFO 2>/dev/null
 probe() { env IRSDE_HBM_NEW=$1 IRSDE_LN_PP=${2:-2} timeout 300 python scripts/hbm_probe.py run /tmp/probe_$1_${2:-2}.pt 2>&1 | tail -1; }
 probe 0; probe 15 2; probe 15 1
-GOOD=15
-if ! python scripts/hbm_probe.py cmp /tmp/probe_0_2.pt /tmp/probe_15_2.pt /tmp/probe_15_1.pt > gpurun_out/hbm_probe.txt 2>&1; then
-  GOOD=0
+GOOD=15; PP1=1
+python scripts/hbm_probe.py cmp /tmp/probe_0_2.pt /tmp/probe_15_1.pt > gpurun_out/hbm_probe.txt 2>&1 || PP1=0
+if ! python scripts/hbm_probe.py cmp /tmp/probe_0_2.pt /tmp/probe_15_2.pt >> gpurun_out/hbm_probe.txt 2>&1; then
+  GOOD=0; PP1=0
   for b in 1 2 4 8; do
     probe $b
     if python scripts/hbm_probe.py cmp /tmp/probe_0_2.pt /tmp/probe_${b}_2.pt >> gpurun_out/hbm_probe.txt 2>&1; then GOOD=$((GOOD | b)); fi
   done
 fi
-cat gpurun_out/hbm_probe.txt | tail -40; echo "GOOD mask = $GOOD"
+cat gpurun_out/hbm_probe.txt | tail -40; echo "GOOD mask = $GOOD, PP=1 usable = $PP1"
 [ "$GOOD" = 0 ] && { echo "no new kernel passed the probe"; exit 1; }
 
 run() { # name mask pp
@@ -33,7 +34,7 @@ M3=$((GOOD & 7))
 for rep in a b; do
   run old_$rep 0 2
   run new_pp2_$rep $GOOD 2
-  run new_pp1_$rep $GOOD 1
+  [ "$PP1" = 1 ] && run new_pp1_$rep $GOOD 1
   [ "$M3" != "$GOOD" ] && [ "$M3" != 0 ] && run nokv_$rep $M3 2
 done 2>&1 | tee gpurun_out/hbm_abab.txt
 # best setting = lowest mean ms/chain among the new ones
@@ -51,6 +52,10 @@ echo "best setting: IRSDE_HBM_NEW=$BM IRSDE_LN_PP=$BP" | tee -a gpurun_out/hbm_a
 export IRSDE_HBM_NEW=$BM IRSDE_LN_PP=$BP
 timeout 400 python bench.py --steps 20 --warmup 5 > gpurun_out/hbm_bench_c2.log 2> gpurun_out/hbm_bench_c2.err
 grep '^{' gpurun_out/hbm_bench_c2.log | tail -1 | cut -c1-400
+timeout 200 python bench.py --workload c4 --steps 5 --warmup 3 --no-cpu > gpurun_out/hbm_bench_c4.log 2> gpurun_out/hbm_bench_c4.err
+grep '^{' gpurun_out/hbm_bench_c4.log | tail -1 | cut -c1-200
+timeout 200 python bench.py --precision fp32x3 --steps 3 --warmup 3 --no-cpu > gpurun_out/hbm_bench_fp32x3.log 2> gpurun_out/hbm_bench_fp32x3.err
+grep '^{' gpurun_out/hbm_bench_fp32x3.log | tail -1 | cut -c1-200
 timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider 2>&1 | tail -15 > gpurun_out/hbm_tests.log; tail -5 gpurun_out/hbm_tests.log
 timeout 400 ncu --set full --clock-control none -k regex:"layernorm|la_kv|la_combine|la_fold|sde_update" -s 40 -c 40 -o /tmp/prof_hbm -f \
   python bench.py --steps 1 --warmup 1 --no-cpu --no-graph > gpurun_out/hbm_ncu.log 2>&1
