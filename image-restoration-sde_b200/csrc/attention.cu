@@ -12,8 +12,9 @@ namespace irsde {
 // Round-2b kernels of this file, one bit each (IRSDE_HBM_NEW; 0 = the round-2a kernels, kept for same-box A/B runs and as
 // the reference scripts/hbm_probe.py compares against).  IRSDE_HBM_DEFAULT is the setting validated on the GPU.
 //   1 = LayerNorm with compile-time lane geometry     2 = la_combine with 128-bit record loads
-//   4 = la_fold with 16 output rows per block          8 = k/v pass with warp-shuffle softmax statistics (2 block barriers)
-#define IRSDE_HBM_DEFAULT 0
+//   4 = la_fold with 16 output rows per block          8 = k/v pass with warp-shuffle, branch-free softmax statistics
+//  16 = la_combine with the records spread over 8 warps (takes precedence over 2)
+#define IRSDE_HBM_DEFAULT 7
 #define IRSDE_LN_PP_DEFAULT 2
 static int hbm_mask_from_env() {
   const char* e = getenv("IRSDE_HBM_NEW");
@@ -537,6 +538,70 @@ __global__ void __launch_bounds__(32) la_combine4_kernel(const float* __restrict
       make_float4(acc.x / S / fN, acc.y / S / fN, acc.z / S / fN, acc.w / S / fN);
 }
 
+// Merge with the records spread over warps.  la_combine4_kernel turned the request storm into 40 wide loads per lane but
+// ncu still shows 21.6 us: what remains is ONE warp walking the <= 64 records in sequence (expf + 5 dependent FMAs each).
+// Here the 8 warps of a block take records w, w + 8, ... (<= 8 each, all loads in flight at once), and warp 0 adds the 8
+// partial (S, ctx) pairs in a fixed order.  The record partition does not depend on the batch, so batch-sharded runs stay
+// bit-identical; the summation order differs from la_combine_kernel (fp32 rounding only).
+__global__ void __launch_bounds__(256) la_combine8_kernel(const float* __restrict__ part, float* __restrict__ ctx, int N, int nblk) {
+  PDL_ENTRY();
+  __shared__ __align__(16) float ms[LA_MAXBLK][4], ss[LA_MAXBLK][4];
+  __shared__ __align__(16) float4 pacc[8][32];
+  __shared__ float pS[8][32];
+  const int bh = blockIdx.x >> 3, b = bh >> 2, h = bh & 3, d0 = (blockIdx.x & 7) * 4;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, dd = lane >> 3, e4 = (lane & 7) * 4;
+  const float* base = part + (long long)b * LA_MAXBLK * LA_REC + h * 1088;
+  const float* cbase = base + 64 + (d0 + dd) * 32 + e4;
+  float4 ck[LA_MAXBLK / 8];
+#pragma unroll
+  for (int j = 0; j < LA_MAXBLK / 8; ++j) {
+    const int k = warp + 8 * j;
+    ck[j] = k < nblk ? *reinterpret_cast<const float4*>(cbase + (long long)k * LA_REC) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (tid < LA_MAXBLK) {
+    float4 m4 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (tid < nblk) {
+      m4 = *reinterpret_cast<const float4*>(base + (long long)tid * LA_REC + d0);
+      s4 = *reinterpret_cast<const float4*>(base + (long long)tid * LA_REC + 32 + d0);
+    }
+    *reinterpret_cast<float4*>(ms[tid]) = m4;
+    *reinterpret_cast<float4*>(ss[tid]) = s4;
+  }
+  __syncthreads();
+  float M = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < LA_MAXBLK; ++k) M = fmaxf(M, ms[k][dd]);
+  float S = 0.f;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < LA_MAXBLK / 8; ++j) {
+    const int k = warp + 8 * j;
+    if (k < nblk) {
+      const float w = expf(ms[k][dd] - M);
+      S += ss[k][dd] * w;
+      acc.x += ck[j].x * w;
+      acc.y += ck[j].y * w;
+      acc.z += ck[j].z * w;
+      acc.w += ck[j].w * w;
+    }
+  }
+  pacc[warp][lane] = acc;
+  pS[warp][lane] = S;
+  __syncthreads();
+  if (warp == 0) {
+    float St = pS[0][lane];
+    float4 a = pacc[0][lane];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      const float4 t = pacc[w][lane];
+      St += pS[w][lane];
+      a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+    }
+    const float fN = (float)N;
+    *reinterpret_cast<float4*>(ctx + (long long)bh * 1024 + (d0 + dd) * 32 + e4) = make_float4(a.x / St / fN, a.y / St / fN, a.z / St / fN, a.w / St / fN);
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) la_out_kernel(const T* __restrict__ qkv, int pitch, const float* __restrict__ ctx,
                                                      T* __restrict__ hidden, int hid_pitch, int N) {
@@ -597,6 +662,11 @@ __device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint3
                : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                : "r"(addr));
 }
+__device__ __forceinline__ float ex2_approx(float x) {  // 2^x, one MUFU (rel. error 2^-22; -inf -> +0)
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ void mma_bf16_16816(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                                uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -649,8 +719,41 @@ __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
   };
+  // SHFL loader: the same 8 vectors per thread, but the 64-bit source address and the shared-memory address are set up ONCE
+  // (vector i of a thread is pixel (tid / 32) + 8 i, channel vector tid % 32: a fixed pitch apart), and the k channels
+  // (vector index < 16) of a pixel past the image get -1e30 (bf16 0xF14A) instead of 0: their exp is 0 and the max is
+  // unaffected, so the statistics loops need no per-pixel bounds checks.  v rows past the image are zero as before.
+  const int lpx0 = tid >> 5, lj = tid & 31;
+  const bf16* const gsrc0 = qkv + ((long long)b * N + lpx0) * pitch + 128 + lj * 8;
+  const long long gstep = (long long)8 * pitch;
+  const uint32_t sdst0 = (uint32_t)__cvta_generic_to_shared(tile) + (uint32_t)((lpx0 * LAM_TP + lj * 8) * 2);
+  const uint32_t kfill = lj < 16 ? 0xF14AF14Au : 0u;
+  auto issue_load_lean = [&](int ch, int buf) {
+    const int n0 = ch * LA_PIX;
+    const bf16* src = gsrc0 + (long long)n0 * pitch;
+    const uint32_t dst = sdst0 + (uint32_t)(buf * LA_PIX * LAM_TP * 2);
+    if (n0 + LA_PIX <= N) {  // whole chunk inside the image (block-uniform): eight plain copies
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(i * 8 * LAM_TP * 2)), "l"(src + i * gstep));
+    } else {
+      const int left = N - n0 - lpx0;  // pixels lpx0 + 8 i with 8 i < left are inside the image
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if (8 * i < left) {
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + (uint32_t)(i * 8 * LAM_TP * 2)), "l"(src + i * gstep));
+        } else {
+          asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(dst + (uint32_t)(i * 8 * LAM_TP * 2)), "r"(kfill) : "memory");
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
 
-  if (c0 < c1) issue_load(c0, 0);
+  if (c0 < c1) {
+    if constexpr (SHFL) issue_load_lean(c0, 0);
+    else issue_load(c0, 0);
+  }
   const int cp2 = (tid & 63) * 2, qtr = tid >> 6;  // stats mapping: 2 channels x 16 pixels per thread
   const float LOG2E = 1.4426950408889634f;
   // SHFL mapping and register-resident running statistics: [0,1] = pair A (lo, hi channel), [2,3] = pair B
@@ -661,50 +764,50 @@ __global__ void __launch_bounds__(256) la_kv_mma_kernel(const bf16* __restrict__
     const bf16* T0 = tile + buf * LA_PIX * LAM_TP;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();  // tile[buf] landed; everyone is done with tile[buf^1] and Ps of the previous chunk
-    if (ch + 1 < c1) issue_load(ch + 1, buf ^ 1);
+    if (ch + 1 < c1) {
+      if constexpr (SHFL) issue_load_lean(ch + 1, buf ^ 1);
+      else issue_load(ch + 1, buf ^ 1);
+    }
     const int nvalid = min(LA_PIX, N - ch * LA_PIX);
     if constexpr (SHFL) {
-      __nv_bfloat162 kA[8], kB[8];
+      // branch-free: rows past the image hold k = -1e30 (see issue_load); ~13 instructions per bf16 pair
+      float k[16][2];
       float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int px = i * 8 + sq;
-        if (px < nvalid) {
-          kA[i] = *reinterpret_cast<const __nv_bfloat162*>(T0 + px * LAM_TP + 2 * pA);
-          kB[i] = *reinterpret_cast<const __nv_bfloat162*>(T0 + px * LAM_TP + 2 * pB);
-          mx[0] = fmaxf(mx[0], __low2float(kA[i]));
-          mx[1] = fmaxf(mx[1], __high2float(kA[i]));
-          mx[2] = fmaxf(mx[2], __low2float(kB[i]));
-          mx[3] = fmaxf(mx[3], __high2float(kB[i]));
-        }
+        const bf16* row = T0 + (i * 8 + sq) * LAM_TP;
+        const __nv_bfloat162 a = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * pA);
+        const __nv_bfloat162 c = *reinterpret_cast<const __nv_bfloat162*>(row + 2 * pB);
+        k[i][0] = __low2float(a); k[i][1] = __high2float(a);
+        k[8 + i][0] = __low2float(c); k[8 + i][1] = __high2float(c);
+        mx[0] = fmaxf(mx[0], k[i][0]); mx[1] = fmaxf(mx[1], k[i][1]);
+        mx[2] = fmaxf(mx[2], k[8 + i][0]); mx[3] = fmaxf(mx[3], k[8 + i][1]);
       }
-      float mn[4], ps[4] = {0.f, 0.f, 0.f, 0.f};
+      float mn[4], mnl[4], ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], o));
         mn[c] = fmaxf(mr[c], mx[c]);
+        mnl[c] = mn[c] * LOG2E;
       }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int px = i * 8 + sq;
-        __nv_bfloat162 qa = __floats2bfloat162_rn(0.f, 0.f), qb = qa;
-        if (px < nvalid) {
-          qa = __floats2bfloat162_rn(exp2f((__low2float(kA[i]) - mn[0]) * LOG2E), exp2f((__high2float(kA[i]) - mn[1]) * LOG2E));
-          qb = __floats2bfloat162_rn(exp2f((__low2float(kB[i]) - mn[2]) * LOG2E), exp2f((__high2float(kB[i]) - mn[3]) * LOG2E));
-          ps[0] += __low2float(qa);   // sum the rounded values the MMA will actually use
-          ps[1] += __high2float(qa);
-          ps[2] += __low2float(qb);
-          ps[3] += __high2float(qb);
-        }
-        *reinterpret_cast<__nv_bfloat162*>(Ps + px * LAM_PP + 2 * pA) = qa;
-        *reinterpret_cast<__nv_bfloat162*>(Ps + px * LAM_PP + 2 * pB) = qb;
+        bf16* prow = Ps + (i * 8 + sq) * LAM_PP;
+        const __nv_bfloat162 qa = __floats2bfloat162_rn(ex2_approx(fmaf(k[i][0], LOG2E, -mnl[0])), ex2_approx(fmaf(k[i][1], LOG2E, -mnl[1])));
+        const __nv_bfloat162 qb = __floats2bfloat162_rn(ex2_approx(fmaf(k[8 + i][0], LOG2E, -mnl[2])), ex2_approx(fmaf(k[8 + i][1], LOG2E, -mnl[3])));
+        ps[0] += __low2float(qa);   // sum the rounded values the MMA will actually use
+        ps[1] += __high2float(qa);
+        ps[2] += __low2float(qb);
+        ps[3] += __high2float(qb);
+        *reinterpret_cast<__nv_bfloat162*>(prow + 2 * pA) = qa;
+        *reinterpret_cast<__nv_bfloat162*>(prow + 2 * pB) = qb;
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
 #pragma unroll
         for (int o = 4; o < 32; o <<= 1) ps[c] += __shfl_xor_sync(0xffffffffu, ps[c], o);
-        const float a = exp2f((mr[c] - mn[c]) * LOG2E);  // 0 on the first chunk
+        const float a = ex2_approx((mr[c] - mn[c]) * LOG2E);  // 0 on the first chunk (mr = -inf)
         sr[c] = sr[c] * a + ps[c];
         mr[c] = mn[c];
         if (sq == 0) alpha_s[2 * (c < 2 ? pA : pB) + (c & 1)] = a;
@@ -844,7 +947,8 @@ void launch_linattn_ctx(const T* qkv, int qkv_pitch, float* partial, float* ctx,
     g_la_attr_done = true;
   }
   launch_la_kv<T>(qkv, qkv_pitch, partial, B, N, nchunks, nblk, smem, st);
-  if (g_hbm_new & 2) pdl_launch(la_combine4_kernel, B * 4 * 8, 32, 0, st, partial, ctx, N, nblk);
+  if (g_hbm_new & 16) pdl_launch(la_combine8_kernel, B * 4 * 8, 256, 0, st, partial, ctx, N, nblk);
+  else if (g_hbm_new & 2) pdl_launch(la_combine4_kernel, B * 4 * 8, 32, 0, st, partial, ctx, N, nblk);
   else pdl_launch(la_combine_kernel, B * 4 * 4, 256, 0, st, partial, ctx, N, nblk);
 }
 template void launch_linattn_ctx<float>(const float*, int, float*, float*, int, int, cudaStream_t);
