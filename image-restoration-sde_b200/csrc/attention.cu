@@ -14,7 +14,7 @@ namespace irsde {
 //   1 = LayerNorm with compile-time lane geometry     2 = la_combine with 128-bit record loads
 //   4 = la_fold with 16 output rows per block          8 = k/v pass with warp-shuffle, branch-free softmax statistics
 //  16 = la_combine with the records spread over 8 warps (takes precedence over 2)
-#define IRSDE_HBM_DEFAULT 7
+#define IRSDE_HBM_DEFAULT 31
 #define IRSDE_LN_PP_DEFAULT 2
 static int hbm_mask_from_env() {
   const char* e = getenv("IRSDE_HBM_NEW");
