@@ -343,3 +343,21 @@ def test_ncu_summariser_refuses_a_capture_without_the_shipped_kernels(tmp_path):
     assert meta["commit"] == "abc" and meta["kernel_mix"] == {"conv_tc_persist_kernel<64, 2, 1, 6>": 1, "conv_tc_persist_kernel<256, 0, 2, 12>": 1}
     bad = subprocess.run([sys.executable, script, str(raw), "--require", r"conv_tc_persist_kernel<\d+, 3[,>]"], capture_output=True, text=True)
     assert bad.returncode == 3 and "no kernel matches" in bad.stderr
+
+
+def test_committed_conv_capture_is_of_the_shipped_conv_kernel_sources():
+    """The roofline's `traffic` comes from profiles/r*_conv_tc_ncu_full_one_step.csv: its .meta.json names the hash of the
+    sources the tcgen05 conv kernel compiles from (conv_tc.cu + common.cuh).  Changing the conv kernel without re-capturing
+    fails here (round 1 shipped a capture of a kernel that was no longer the benchmarked one)."""
+    import glob
+    import importlib.util
+    import json
+    spec = importlib.util.spec_from_file_location("irsde_build", os.path.join(ROOT, "image-restoration-sde_b200", "build.py"))
+    build = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(build)
+    metas = sorted(m for m in glob.glob(os.path.join(ROOT, "profiles", "r*_conv_tc_ncu_full_one_step.meta.json")) if "_v1_" not in m)
+    assert metas, "no committed conv capture"
+    meta = json.load(open(metas[-1]))
+    assert meta["conv_tc_sha256"] == build.conv_tc_sha256()
+    mix = meta["kernel_mix"]
+    assert any(re.match(r"conv_tc_persist_kernel<\d+, 2,", k) for k in mix) and any(k.startswith("conv_tc_persist_kernel<256, 0, 2") for k in mix)
