@@ -193,7 +193,7 @@ def _reference_objects(wl, device):
     return sde, net
 
 
-def cpu_reference_sample(wl, steps_per_sample=3, threads=None, objs=None):
+def cpu_reference_sample(wl, steps_per_sample=3, threads=None, objs=None, prewarm=True):
     """The reference on host cores (PyTorch CPU fp32, all usable threads).  Bounded sample = `steps_per_sample` steps of
     the reference's own reverse loop on ONE image of the workload; every step of the chain costs the same, so
     img/s = 1 / (T * s_per_step).  Returns (images_per_s, seconds, description, kind)."""
@@ -210,6 +210,8 @@ def cpu_reference_sample(wl, steps_per_sample=3, threads=None, objs=None):
         xT = lq + torch.randn(lq.shape, generator=g) * sde.max_sigma
         sde.set_mu(lq)
         with torch.no_grad():
+            if prewarm:
+                getattr(sde, "reverse_" + w["mode"])(xT, T=1)   # untimed: thread pool / allocator warm-up
             t0 = time.perf_counter()
             getattr(sde, "reverse_" + w["mode"])(xT, T=steps_per_sample)
             dt = time.perf_counter() - t0
@@ -246,7 +248,7 @@ def run_reference(args):
     objs = _reference_objects(wl, torch.device("cpu"))
     vals, secs, kind, sample = [], [], "port", ""
     for i in range(args.warmup + args.steps):
-        v, dt, sample, kind = cpu_reference_sample(wl, steps_per_sample=1 if i < args.warmup else 2, objs=objs)
+        v, dt, sample, kind = cpu_reference_sample(wl, steps_per_sample=1 if i < args.warmup else 2, objs=objs, prewarm=False)
         if i >= args.warmup:
             vals.append(v); secs.append(dt)
     value = len(vals) / sum(1.0 / v for v in vals)  # harmonic mean = total images / total time
@@ -536,7 +538,8 @@ def run_b200(args):
     # ---- (4) CPU baseline (rank 0, N=1 only): bounded sample of the same workload on host cores
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and w["kind"] == "unet":
-        v, dt, sample, kind = cpu_reference_sample(wl, steps_per_sample=4)
+        # about 10 s of host work: 12 sampler steps of one 256x256 image (fewer at larger sizes), after one untimed step
+        v, dt, sample, kind = cpu_reference_sample(wl, steps_per_sample=max(3, int(round(12 * 65536.0 / (w["H"] * w["W"])))))
         cpu = {"value": v, "unit": "images/s", "cores": usable_cores(), "kind": kind, "sample": sample, "seconds": dt}
 
     if rank == 0:
