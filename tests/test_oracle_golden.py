@@ -211,3 +211,25 @@ def test_unet_ch_mult_variant_vs_reference():
     m.load_state_dict(g["state"], strict=True)
     m2 = irsde_b200.ConditionalUNet(c["in_nc"], c["out_nc"], c["nf"], c["ch_mult"])   # positional, like the reference signature
     assert m2.depth == 3 and list(m2.state_dict().keys()) == list(g["state"].keys())
+
+
+def test_oracle_per_layer_trace_vs_reference_hooks():
+    """The oracle's `trace=` checkpoints (what the GPU per-layer parity reports compare with) against forward hooks on the
+    reference's own modules (tests/golden/make_golden_layers.py): every layer's fingerprint - shape, fp64 sum / abs-sum,
+    <= 512 strided elements - for the conditional UNet (ragged input) and the denoising-sde variant (full Attention)."""
+    G = torch.load(os.path.join(os.path.dirname(__file__), "golden", "reference_golden_layers.pt"), weights_only=True)
+    for variant, g in (("conditional", G["cond"]), ("denoising", G["denoising"])):
+        c = g["cfg"]
+        tr = {}
+        y = O.unet_forward(g["state"], g["x"], g.get("cond"), g["t"], c["nf"], c["depth"], variant=variant, trace=tr)
+        assert (y - g["y"]).abs().max().item() < 1e-5
+        assert set(tr.keys()) == set(g["layers"].keys()), (sorted(set(tr) ^ set(g["layers"])))
+        for key, fp in g["layers"].items():
+            t = tr[key]
+            assert list(t.shape) == fp["shape"].tolist(), key
+            f = t.reshape(-1)
+            n = f.numel()
+            scale = max(1.0, float(fp["abssum"]) / n)
+            assert (f[::int(fp["stride"])] - fp["sample"]).abs().max().item() < 1e-5 * max(1.0, float(fp["sample"].abs().max())), key
+            assert abs(float(f.double().sum()) - float(fp["sum"])) < 2e-6 * n * scale, key
+            assert abs(float(f.double().abs().sum()) - float(fp["abssum"])) < 2e-6 * n * scale, key
